@@ -1,0 +1,377 @@
+// hqr.cuh -- eigenvalues of a complex upper Hessenberg matrix by shifted QR, one CTA per matrix.
+// This is the ZHSEQR stage of the ZGEEV the reference calls (temporal.f90:803, spatial.f90:1043),
+// eigenvalues only (the Schur form is not kept; eigenvectors come from inverse iteration, evec.cuh).
+//
+// Design (B200-first, not LAPACK's blocking):
+//   * small-bulge MULTISHIFT sweeps: a chain of ns single-shift bulges (2-element reflectors,
+//     spaced two rows apart) is chased down the active block;
+//   * the chain is chased inside a W x W diagonal WINDOW held in shared memory (all bulges step
+//     simultaneously: reflector generation / left application / right application are three
+//     barrier-separated phases), the reflectors of the pass are recorded, and then streamed over
+//     the off-window slabs straight from L2/HBM -- thread per column (left slab) or per row
+//     (right slab), bulge-major order with a register carry, so every slab element is loaded and
+//     stored once per bulge;
+//   * active blocks that fit the window are finished entirely in shared memory by a single-shift
+//     Wilkinson QR (ZLAHQR logic: conservative Ahues-Tisseur deflation test, exceptional shifts);
+//     the same routine provides the ns shifts (eigenvalues of the trailing ns x ns block).
+// Eigenvalues only => all updates are restricted to the active block [L, I].
+#pragma once
+#include "common.cuh"
+
+namespace stab {
+
+struct Refl { cplx v2; cplx tau; };   // H = I - tau [1;v2][1;v2]^H
+
+struct Grp { int tid, nt; bool warp; };
+SD_DEV void grp_sync(const Grp& g) {
+#ifndef STAB_EMU
+  if (g.warp) __syncwarp(); else __syncthreads();
+#else
+  (void)g;
+#endif
+}
+
+// 2-element ZLARFG: on return x1 := beta (real), returns {v2, tau}
+SD_DEV Refl larfg2(cplx& x1, cplx x2) {
+  Refl r; r.v2 = mk(0.0, 0.0); r.tau = mk(0.0, 0.0);
+  double xn2 = abs2(x2);
+  if (xn2 == 0.0 && x1.im == 0.0) return r;
+  // scale to avoid spurious over/underflow in the squares
+  double sc = fmax(cabs1(x1), cabs1(x2));
+  cplx a = mk(x1.re / sc, x1.im / sc), b = mk(x2.re / sc, x2.im / sc);
+  double nrm = sqrt(abs2(a) + abs2(b));
+  double beta = -copysign(nrm, a.re);
+  r.tau = mk((beta - a.re) / beta, -a.im / beta);
+  r.v2 = cdiv(b, mk(a.re - beta, a.im));
+  x1 = mk(beta * sc, 0.0);
+  return r;
+}
+
+SD_DEV void apply_left(const Refl& r, cplx& x1, cplx& x2) {    // [x1;x2] := (I - conj(tau) v v^H) [x1;x2]
+  cplx s = x1; fma_acc_conj(s, r.v2, x2);
+  s = conj(r.tau) * s;
+  x1 -= s;
+  x2 -= s * r.v2;
+}
+SD_DEV void apply_right(const Refl& r, cplx& x1, cplx& x2) {   // [x1 x2] := [x1 x2] (I - tau v v^H)
+  cplx s = x1; fma_acc(s, x2, r.v2);
+  s = s * r.tau;
+  x1 -= s;
+  x2 -= mulc(s, r.v2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chase of a bulge chain on a matrix S held in shared memory.  S(r,c) = S[r + c*lds] maps to
+// global indices (g0+r, g0+c).  Bulge b at time t sits at k = L + t - 2b and is active while
+// 0 <= t-2b <= I-1-L.  Left applications cover local columns <= chi, right applications local
+// rows >= rlo.  `rec` (optional) receives the reflectors, (t-ta)*ns + b.
+// ---------------------------------------------------------------------------------------------
+SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int L, int I,
+                  const cplx* shifts, int ns, int ta, int tb, Refl* rec, Refl* cur) {
+  const int smax = I - 1 - L;
+  for (int t = ta; t < tb; ++t) {
+    for (int b = g.tid; b < ns; b += g.nt) {
+      const int s = t - 2 * b;
+      Refl r; r.v2 = mk(0.0, 0.0); r.tau = mk(0.0, 0.0);
+      if (s >= 0 && s <= smax) {
+        const int kl = L + s - g0;
+        if (s == 0) {
+          cplx x1 = S[kl + kl * lds] - shifts[b];
+          cplx x2 = S[kl + 1 + kl * lds];
+          r = larfg2(x1, x2);
+        } else {
+          cplx x1 = S[kl + (kl - 1) * lds];
+          cplx x2 = S[kl + 1 + (kl - 1) * lds];
+          r = larfg2(x1, x2);
+          S[kl + (kl - 1) * lds] = x1;
+          S[kl + 1 + (kl - 1) * lds] = mk(0.0, 0.0);
+        }
+      }
+      cur[b] = r;
+      if (rec) rec[(t - ta) * ns + b] = r;
+    }
+    grp_sync(g);
+    const int ncol = chi + 1;
+    for (int q = g.tid; q < ns * ncol; q += g.nt) {
+      const int b = q / ncol, col = q - b * ncol;
+      const int s = t - 2 * b;
+      if (s < 0 || s > smax) continue;
+      const int kl = L + s - g0;
+      if (col < kl) continue;
+      const Refl r = cur[b];
+      if (is_zero(r.tau)) continue;
+      cplx x1 = S[kl + col * lds], x2 = S[kl + 1 + col * lds];
+      apply_left(r, x1, x2);
+      S[kl + col * lds] = x1; S[kl + 1 + col * lds] = x2;
+    }
+    grp_sync(g);
+    for (int q = g.tid; q < ns * ncol; q += g.nt) {
+      const int b = q / ncol, row = q - b * ncol;
+      const int s = t - 2 * b;
+      if (s < 0 || s > smax) continue;
+      const int kl = L + s - g0;
+      int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
+      if (row < rlo || row > rmax) continue;
+      const Refl r = cur[b];
+      if (is_zero(r.tau)) continue;
+      cplx x1 = S[row + kl * lds], x2 = S[row + (kl + 1) * lds];
+      apply_right(r, x1, x2);
+      S[row + kl * lds] = x1; S[row + (kl + 1) * lds] = x2;
+    }
+    grp_sync(g);
+  }
+}
+
+// ZLAHQR's small-subdiagonal test at (k, k-1) on a matrix accessed through `at(r,c)`;
+// lo/hi bound the neighbours consulted when both diagonal entries vanish.
+template <class At>
+SD_DEV bool negligible_subdiag(const At& at, int k, int lo, int hi, double smlnum) {
+  cplx hkk1 = at(k, k - 1);
+  double a1 = cabs1(hkk1);
+  if (a1 <= smlnum) return true;
+  cplx hkk = at(k, k), hk1k1 = at(k - 1, k - 1);
+  double tst = cabs1(hk1k1) + cabs1(hkk);
+  if (tst == 0.0) {
+    if (k - 2 >= lo) tst += cabs1(at(k - 1, k - 2));
+    if (k + 1 <= hi) tst += cabs1(at(k + 1, k));
+  }
+  if (a1 <= SD_ULP * tst) {
+    double b1 = cabs1(at(k - 1, k));
+    double ab = fmax(a1, b1), ba = fmin(a1, b1);
+    double d1 = cabs1(hkk), d2 = cabs1(hk1k1 - hkk);
+    double aa = fmax(d1, d2), bb = fmin(d1, d2);
+    double s = aa + ab;
+    if (ba * (ab / s) <= fmax(smlnum, SD_ULP * (bb * (aa / s)))) return true;
+  }
+  return false;
+}
+
+struct SmemAt { const cplx* S; int lds; SD_DEV cplx operator()(int r, int c) const { return S[r + c * lds]; } };
+struct GlobAt { const cplx* H; int ldh; SD_DEV cplx operator()(int r, int c) const { return H[r + (size_t)c * ldh]; } };
+
+// Wilkinson shift of ZLAHQR from the trailing 2x2 of the active block ending at I
+SD_DEV cplx wilkinson_shift(cplx h11, cplx h12, cplx h21, cplx h22) {
+  cplx t = h22;
+  cplx u = csqrt_(h12) * csqrt_(h21);
+  double s = cabs1(u);
+  if (s != 0.0) {
+    cplx x = 0.5 * (h11 - t);
+    double sx = cabs1(x);
+    s = fmax(s, sx);
+    cplx xs = mk(x.re / s, x.im / s), us = mk(u.re / s, u.im / s);
+    cplx y = s * csqrt_(xs * xs + us * us);
+    if (sx > 0.0) {
+      if ((x.re / sx) * y.re + (x.im / sx) * y.im < 0.0) y = -y;
+    }
+    t = t - u * cdiv(u, x + y);
+  }
+  return t;
+}
+
+struct SmallCtl { int L; int pad; cplx shift; };
+
+// All eigenvalues of the m x m upper Hessenberg matrix S (shared memory), single-shift QR.
+// Returns the number of eigenvalues that failed to converge (0 = success); converged ones are in
+// wout[...], for failures wout holds the current diagonal.
+SD_DEV int smem_hqr(const Grp& g, cplx* S, int lds, int m, cplx* wout, SmallCtl* ctl, Refl* cur) {
+  const double smlnum = SD_SAFMIN * ((double)m / SD_ULP);
+  int I = m - 1;
+  int its = 0;
+  const int itmax = 30 * (m > 10 ? m : 10);
+  int total = 0;
+  SmemAt at; at.S = S; at.lds = lds;
+  while (I >= 0) {
+    if (g.tid == 0) {
+      int L = 0;
+      for (int k = I; k >= 1; --k) {
+        if (negligible_subdiag(at, k, 0, m - 1, smlnum)) { L = k; break; }
+      }
+      if (L > 0) S[L + (L - 1) * lds] = mk(0.0, 0.0);
+      ctl->L = L;
+      if (L < I) {
+        cplx t;
+        if (its == 10) {
+          t = mk(0.75 * fabs(S[L + 1 + L * lds].re), 0.0) + S[L + L * lds];
+        } else if (its == 20) {
+          t = mk(0.75 * fabs(S[I + (I - 1) * lds].re), 0.0) + S[I + I * lds];
+        } else {
+          t = wilkinson_shift(S[I - 1 + (I - 1) * lds], S[I - 1 + I * lds], S[I + (I - 1) * lds], S[I + I * lds]);
+        }
+        ctl->shift = t;
+      } else {
+        wout[I] = S[I + I * lds];
+      }
+    }
+    grp_sync(g);
+    const int L = ctl->L;
+    if (L >= I) { I -= 1; its = 0; grp_sync(g); continue; }
+    if (total++ >= itmax) {
+      // give up: report the diagonal for what is left
+      for (int k = g.tid; k <= I; k += g.nt) wout[k] = S[k + k * lds];
+      grp_sync(g);
+      return I + 1;
+    }
+    its += 1;
+    chase(g, S, lds, 0, L, I, L, I, &ctl->shift, 1, 0, I - L, nullptr, cur);
+  }
+  return 0;
+}
+
+struct HqrSmem {
+  cplx* win;     // W * ldw
+  int ldw, W;
+  Refl* rec;     // steps_max * ns_max
+  int steps_max, ns_max;
+  Refl* cur;     // ns_max
+  cplx* shifts;  // ns_max
+  cplx* sm;      // ns_max * (ns_max + 1)   trailing block for the shift computation
+  SmallCtl* ctl;
+};
+
+// One multishift sweep over the active block [L, I] of the global Hessenberg matrix H.
+SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, int L, int I, int ns) {
+  Grp g; g.tid = c.tid; g.nt = c.nt; g.warp = false;
+  const int W = sh.W, ldw = sh.ldw;
+  const int T = I - L + 2 * ns - 2;
+  int ta = 0;
+  while (ta < T) {
+    int tb, g0;
+    if (ta == 0) {
+      int first = W - 2; if (first > sh.steps_max) first = sh.steps_max;
+      tb = first; g0 = L;
+    } else {
+      int adv = W - 2 * ns - 1; if (adv > sh.steps_max) adv = sh.steps_max;
+      tb = ta + adv; g0 = L + ta - 2 * (ns - 1) - 1;
+    }
+    if (tb > T) tb = T;
+    int g1 = L + tb + 1; if (g1 > I) g1 = I;
+    const int wsz = g1 - g0 + 1;
+    // load the window (upper Hessenberg part plus the two sub-diagonals that can hold bulges)
+    for (int q = c.tid; q < wsz * wsz; q += c.nt) {
+      const int col = q / wsz, row = q - col * wsz;
+      sh.win[row + col * ldw] = (row <= col + 2) ? H[(g0 + row) + (size_t)(g0 + col) * ldh] : mk(0.0, 0.0);
+    }
+    cta_sync();
+    chase(g, sh.win, ldw, g0, 0, wsz - 1, L, I, sh.shifts, ns, ta, tb, sh.rec, sh.cur);
+    for (int q = c.tid; q < wsz * wsz; q += c.nt) {
+      const int col = q / wsz, row = q - col * wsz;
+      if (row <= col + 2) H[(g0 + row) + (size_t)(g0 + col) * ldh] = sh.win[row + col * ldw];
+    }
+    const int smax = I - 1 - L;
+    // left slab: rows [g0, g1], columns (g1, I]; thread per column, bulge-major with carry
+    for (int col = g1 + 1 + c.tid; col <= I; col += c.nt) {
+      cplx* hc = H + (size_t)col * ldh;
+      for (int b = 0; b < ns; ++b) {
+        int t0 = ta > 2 * b ? ta : 2 * b;
+        int t1 = tb - 1; if (t1 > 2 * b + smax) t1 = 2 * b + smax;
+        if (t0 > t1) continue;
+        int k = L + t0 - 2 * b;
+        cplx x = hc[k];
+        for (int t = t0; t <= t1; ++t, ++k) {
+          cplx y = hc[k + 1];
+          const Refl r = sh.rec[(t - ta) * ns + b];
+          if (!is_zero(r.tau)) apply_left(r, x, y);
+          hc[k] = x;
+          x = y;
+        }
+        hc[k] = x;
+      }
+    }
+    // right slab: rows [L, g0), columns of the chain; thread per row
+    for (int row = L + c.tid; row < g0; row += c.nt) {
+      cplx* hr = H + row;
+      for (int b = 0; b < ns; ++b) {
+        int t0 = ta > 2 * b ? ta : 2 * b;
+        int t1 = tb - 1; if (t1 > 2 * b + smax) t1 = 2 * b + smax;
+        if (t0 > t1) continue;
+        int k = L + t0 - 2 * b;
+        cplx x = hr[(size_t)k * ldh];
+        for (int t = t0; t <= t1; ++t, ++k) {
+          cplx y = hr[(size_t)(k + 1) * ldh];
+          const Refl r = sh.rec[(t - ta) * ns + b];
+          if (!is_zero(r.tau)) apply_right(r, x, y);
+          hr[(size_t)k * ldh] = x;
+          x = y;
+        }
+        hr[(size_t)k * ldh] = x;
+      }
+    }
+    cta_sync();
+    ta = tb;
+  }
+}
+
+// Eigenvalues of the Hessenberg matrix H (entries below the first subdiagonal must be zero) on
+// [ilo, ihi]; entries outside are read off the diagonal.  Returns 0 or the number of unconverged
+// eigenvalues (LAPACK-style info > 0).
+SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int ilo, int ihi, cplx* w) {
+  Grp g; g.tid = c.tid; g.nt = c.nt; g.warp = false;
+  for (int j = c.tid; j < n; j += c.nt)
+    if (j < ilo || j > ihi) w[j] = H[j + (size_t)j * ldh];
+  const int nh = ihi - ilo + 1;
+  const double smlnum = SD_SAFMIN * ((double)nh / SD_ULP);
+  GlobAt at; at.H = H; at.ldh = ldh;
+  int I = ihi;
+  int stagn = 0;
+  long total = 0;
+  const long itmax = 30L * (nh > 10 ? nh : 10);
+  int info = 0;
+  cta_sync();
+  while (I >= ilo) {
+    // largest k in (ilo, I] whose subdiagonal is negligible
+    int best = ilo;
+    for (int k = ilo + 1 + c.tid; k <= I; k += c.nt)
+      if (negligible_subdiag(at, k, ilo, ihi, smlnum)) best = k;
+    const int L = cta_max_i(c, best);
+    if (L > ilo && c.tid == 0) H[L + (size_t)(L - 1) * ldh] = mk(0.0, 0.0);
+    if (L == I) {
+      if (c.tid == 0) w[I] = H[I + (size_t)I * ldh];
+      I -= 1; stagn = 0;
+      cta_sync();
+      continue;
+    }
+    const int m = I - L + 1;
+    if (m <= sh.W) {
+      // finish this block in shared memory
+      for (int q = c.tid; q < m * m; q += c.nt) {
+        const int col = q / m, row = q - col * m;
+        sh.win[row + col * sh.ldw] = (row <= col + 1) ? H[(L + row) + (size_t)(L + col) * ldh] : mk(0.0, 0.0);
+      }
+      cta_sync();
+      int bad = smem_hqr(g, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur);
+      if (bad) info += bad;
+      I = L - 1; stagn = 0;
+      cta_sync();
+      continue;
+    }
+    if (total++ >= itmax) { info += I - ilo + 1; for (int k = ilo + c.tid; k <= I; k += c.nt) w[k] = H[k + (size_t)k * ldh]; break; }
+    // number of shifts for this block
+    int ns = sh.ns_max;
+    if (m < 4 * ns) ns = m / 4;
+    if (ns < 2) ns = 2;
+    stagn += 1;
+    if (stagn % 6 == 0) {
+      // exceptional shifts (ZLAQR0 style): diagonal entry plus 0.75 |subdiagonal|
+      for (int b = c.tid; b < ns; b += c.nt) {
+        const int k = I - b;
+        sh.shifts[b] = H[k + (size_t)k * ldh] + mk(0.75 * cabs1(H[k + (size_t)(k - 1) * ldh]), 0.0);
+      }
+      cta_sync();
+    } else {
+      const int k0 = I - ns + 1;
+      const int lds = sh.ns_max + 1;
+      for (int q = c.tid; q < ns * ns; q += c.nt) {
+        const int col = q / ns, row = q - col * ns;
+        sh.sm[row + col * lds] = (row <= col + 1) ? H[(k0 + row) + (size_t)(k0 + col) * ldh] : mk(0.0, 0.0);
+      }
+      cta_sync();
+      smem_hqr(g, sh.sm, lds, ns, sh.shifts, sh.ctl, sh.cur);
+      cta_sync();
+    }
+    sweep_multishift(c, sh, H, ldh, L, I, ns);
+  }
+  cta_sync();
+  return info;
+}
+
+}  // namespace stab

@@ -1,0 +1,307 @@
+// kernels.cuh -- __global__ entry points (sm_100a).  Each eigen-stage kernel is "one CTA per sweep
+// point"; the assembly kernels are grid-wide streaming writers.
+#pragma once
+#include "common.cuh"
+#include "tables.cuh"
+#include "assemble.cuh"
+#include "balance.cuh"
+#include "hessenberg.cuh"
+#include "hqr.cuh"
+#include "evec.cuh"
+#include "lu.cuh"
+
+namespace stab {
+
+struct SweepDev {            // per-point sweep values (device arrays; Re/Ma may be null)
+  const cplx* s1;            // alpha (temporal) or omega (spatial)
+  const cplx* s2;            // beta
+  const double* Re;
+  const double* Ma;
+};
+
+SD_DEV Phys point_phys(const Phys& base, const SweepDev& sw, int p) {
+  Phys q = base;
+  if (sw.Re) q.Re = sw.Re[p];
+  if (sw.Ma) q.Ma = sw.Ma[p];
+  q.navier = !(q.Re >= 1.0e98 || q.Re == 0.0);        // temporal.f90:88-91
+  return q;
+}
+
+// ---- stage 1a: node coefficients ---------------------------------------------------------------
+// coef layout temporal: [p][node][3][25]; spatial: [p][node][6][25] (C0.c1, C0.c2, C0.c0, C1.c1, C1.c0, C2.c0)
+__global__ void k_node_coef_temporal(GridDev g, Phys base, SweepDev sw, int p0, int apply_b0inv, cplx* coef, cplx* b0blk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (i >= g.ny) return;
+  Phys ph = point_phys(base, sw, p0 + p);
+  NodeIn q = load_node(g, i);
+  Tables t;
+  node_tables_temporal(q, ph, t);
+  PointTemporal pt; pt.alpha = sw.s1[p0 + p]; pt.beta = sw.s2[p0 + p];
+  NodeCoef3 o;
+  node_coef_temporal(t, i, g.ny, g.wallt, g.deta[i], g.d2eta[i], pt, apply_b0inv != 0, o);
+  cplx* dst = coef + ((size_t)p * g.ny + i) * 75;
+  for (int k = 0; k < 25; ++k) { dst[k] = o.c1[k]; dst[25 + k] = o.c2[k]; dst[50 + k] = o.c0[k]; }
+  if (b0blk) node_b0_temporal(t, i, g.ny, g.wallt, b0blk + ((size_t)p * g.ny + i) * 25);
+}
+
+__global__ void k_node_coef_spatial(GridDev g, Phys base, SweepDev sw, int p0, cplx* coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (i >= g.ny) return;
+  Phys ph = point_phys(base, sw, p0 + p);
+  NodeIn q = load_node(g, i);
+  Tables t;
+  node_tables_spatial(q, ph, t);
+  PointSpatial pt; pt.omega = sw.s1[p0 + p]; pt.beta = sw.s2[p0 + p];
+  NodeCoefSpatial o;
+  node_coef_spatial(t, i, g.ny, g.wallt, g.top, g.deta[i], g.d2eta[i], pt, o);
+  cplx* dst = coef + ((size_t)p * g.ny + i) * 150;
+  for (int k = 0; k < 25; ++k) {
+    dst[k] = o.C0.c1[k]; dst[25 + k] = o.C0.c2[k]; dst[50 + k] = o.C0.c0[k];
+    dst[75 + k] = o.C1c1[k]; dst[100 + k] = o.C1c0[k]; dst[125 + k] = o.C2c0[k];
+  }
+}
+
+// ---- stage 1b: dense operator streaming writers -------------------------------------------------
+// One thread per matrix row r = 5 i + e; a CTA covers 128 rows and JT node-columns (5 JT matrix
+// columns).  For a fixed column consecutive threads write consecutive rows: full 16-byte
+// coalesced stores; D1/D2 are read through the read-only path (L1/L2 resident, 128 KB each).
+// Algorithmic traffic: 16 n^2 bytes written per matrix; HBM-bound.
+constexpr int ASM_ROWS = 128;
+constexpr int ASM_JT = 8;
+
+__global__ void __launch_bounds__(ASM_ROWS) k_assemble_temporal(GridDev g, const cplx* __restrict__ coef, cplx* __restrict__ M, size_t mstride) {
+  const int n = 5 * g.ny, ny = g.ny;
+  const int r = blockIdx.x * ASM_ROWS + threadIdx.x;
+  const int p = blockIdx.z;
+  if (r >= n) return;
+  const int i = r / 5, e = r - 5 * i;
+  const cplx* cf = coef + ((size_t)p * ny + i) * 75 + e * 5;
+  cplx c1[5], c2[5], c0[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) { c1[v] = cf[v]; c2[v] = cf[25 + v]; c0[v] = cf[50 + v]; }
+  cplx* out = M + (size_t)p * mstride + r;
+  const int j0 = blockIdx.y * ASM_JT;
+  const bool wallrow = (g.wallt == 2 && i == ny - 1);
+#pragma unroll 2
+  for (int j = j0; j < j0 + ASM_JT && j < ny; ++j) {
+    const double d1 = __ldg(g.D1 + i + (size_t)j * ny);
+    const double d2 = __ldg(g.D2 + i + (size_t)j * ny);
+    const double d2w = wallrow ? __ldg(g.Dt2w + j) : d2;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      cplx a = c1[v] * d1 + c2[v] * ((v == 4) ? d2w : d2);
+      if (i == j) a += c0[v];
+      out[(size_t)(5 * j + v) * n] = a;
+    }
+  }
+}
+
+// Spatial: C (n x n, ldc = n) <- C0 ; companion (2n x 2n, ld 2n): top <- [-C1 | -C2], bottom <- [I | 0]
+__global__ void __launch_bounds__(ASM_ROWS) k_assemble_spatial(GridDev g, const cplx* __restrict__ coef, cplx* __restrict__ C, size_t cstride,
+                                                               cplx* __restrict__ B, size_t bstride) {
+  const int n = 5 * g.ny, ny = g.ny, n2 = 2 * n;
+  const int r = blockIdx.x * ASM_ROWS + threadIdx.x;
+  const int p = blockIdx.z;
+  if (r >= n) return;
+  const int i = r / 5, e = r - 5 * i;
+  const cplx* cf = coef + ((size_t)p * ny + i) * 150 + e * 5;
+  cplx c1[5], c2[5], c0[5], k1[5], k0[5], q0[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) { c1[v] = cf[v]; c2[v] = cf[25 + v]; c0[v] = cf[50 + v]; k1[v] = cf[75 + v]; k0[v] = cf[100 + v]; q0[v] = cf[125 + v]; }
+  cplx* outC = C + (size_t)p * cstride + r;
+  cplx* outB = B + (size_t)p * bstride + r;
+  const int j0 = blockIdx.y * ASM_JT;
+  const bool wallrow = (g.wallt == 2 && i == ny - 1);
+  const cplx zero = mk(0.0, 0.0);
+  for (int j = j0; j < j0 + ASM_JT && j < ny; ++j) {
+    const double d1 = __ldg(g.D1 + i + (size_t)j * ny);
+    const double d2 = __ldg(g.D2 + i + (size_t)j * ny);
+    const double d2w = wallrow ? __ldg(g.Dt2w + j) : d2;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      const int col = 5 * j + v;
+      cplx a = c1[v] * d1 + c2[v] * ((v == 4) ? d2w : d2);
+      cplx b1 = k1[v] * d1;
+      cplx b2 = zero;
+      if (i == j) { a += c0[v]; b1 += k0[v]; b2 = q0[v]; }
+      outC[(size_t)col * n] = a;
+      outB[(size_t)col * n2] = b1;                          // -C1
+      outB[(size_t)(n + col) * n2] = b2;                    // -C2
+      outB[(size_t)col * n2 + n] = (col == r) ? mk(1.0, 0.0) : zero;   // identity block
+      outB[(size_t)(n + col) * n2 + n] = zero;
+    }
+  }
+}
+
+// element-wise inspection kernel: A0 (no B0^-1) and B0, or C0/C1/C2 with the reference's signs
+__global__ void k_inspect_temporal(GridDev g, const cplx* coef, const cplx* b0blk, cplx* A0, cplx* B0) {
+  const int n = 5 * g.ny;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * n) return;
+  const int r = (int)(idx % n), c = (int)(idx / n);
+  const int i = r / 5, e = r % 5, j = c / 5, v = c % 5;
+  const cplx* cf = coef + (size_t)i * 75;
+  A0[idx] = op_element(cf, cf + 25, cf + 50, g, i, e, j, v);
+  B0[idx] = (i == j) ? b0blk[(size_t)i * 25 + e * 5 + v] : mk(0.0, 0.0);
+}
+
+__global__ void k_inspect_spatial(GridDev g, const cplx* coef, cplx* C0, cplx* C1, cplx* C2) {
+  const int n = 5 * g.ny;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * n) return;
+  const int r = (int)(idx % n), c = (int)(idx / n);
+  const int i = r / 5, e = r % 5, j = c / 5, v = c % 5;
+  const cplx* cf = coef + (size_t)i * 150;
+  C0[idx] = op_element(cf, cf + 25, cf + 50, g, i, e, j, v);
+  const int k = e * 5 + v;
+  cplx b1 = cf[75 + k] * g.D1[i + (size_t)j * g.ny];
+  cplx b2 = mk(0.0, 0.0);
+  if (i == j) { b1 += cf[100 + k]; b2 = cf[125 + k]; }
+  C1[idx] = -b1;
+  C2[idx] = -b2;
+}
+
+// ---- stage 2 (spatial): LU reduce ---------------------------------------------------------------
+__global__ void k_lu(cplx* C, size_t cstride, int n, cplx* B, size_t bstride, int nrhs, int ldb, int* info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* red = reinterpret_cast<double*>(smem_raw);
+  cplx* sl = reinterpret_cast<cplx*>(smem_raw + 160 * sizeof(double));
+  Cta c = make_cta(red);
+  const int p = blockIdx.x;
+  int r = cta_lu_solve(c, C + (size_t)p * cstride, n, n, B + (size_t)p * bstride, nrhs, ldb, sl);
+  if (threadIdx.x == 0) info[p] = r;
+}
+
+// ---- stage 3a: balance --------------------------------------------------------------------------
+__global__ void k_balance(cplx* A, size_t astride, int n, double* scale, int* cnt, int* ilohi) {
+  __shared__ double red[160];
+  Cta c = make_cta(red);
+  const int p = blockIdx.x;
+  int ilo, ihi;
+  cta_balance(c, A + (size_t)p * astride, n, n, scale + (size_t)p * n, cnt + (size_t)p * n, ilo, ihi);
+  if (threadIdx.x == 0) { ilohi[2 * p] = ilo; ilohi[2 * p + 1] = ihi; }
+}
+
+// ---- stage 3b: Hessenberg -----------------------------------------------------------------------
+__global__ void k_hessenberg(cplx* A, size_t astride, int n, const int* ilohi, cplx* tau) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* red = reinterpret_cast<double*>(smem_raw);
+  cplx* sv = reinterpret_cast<cplx*>(smem_raw + 160 * sizeof(double));
+  cplx* sy = sv + n;
+  Cta c = make_cta(red);
+  const int p = blockIdx.x;
+  cta_hessenberg(c, A + (size_t)p * astride, n, n, ilohi[2 * p], ilohi[2 * p + 1], tau + (size_t)p * n, sv, sy);
+}
+
+// ---- stage 3c: prepare the QR operand: Hq := upper Hessenberg part of A (zeros below), plus the
+// infinity norm of H for the inverse-iteration tolerances.  Hq may alias A (eigenvalues-only path).
+__global__ void k_prep_qr(const cplx* A, size_t astride, cplx* Hq, size_t hstride, int n, double* hnorm) {
+  __shared__ double red[160];
+  Cta c = make_cta(red);
+  const int p = blockIdx.x;
+  const cplx* a = A + (size_t)p * astride;
+  cplx* h = Hq + (size_t)p * hstride;
+  double mx = 0.0;
+  for (int r = c.tid; r < n; r += c.nt) {
+    double s = 0.0;
+    for (int j = (r > 0 ? r - 1 : 0); j < n; ++j) s += cabs(a[r + (size_t)j * n]);
+    mx = fmax(mx, s);
+  }
+  double dummy = 0.0;
+  cta_max2(c, mx, dummy);
+  if (c.tid == 0) hnorm[p] = mx;
+  for (int j = 0; j < n; ++j)
+    for (int r = c.tid; r < n; r += c.nt) {
+      cplx v = a[r + (size_t)j * n];
+      if (r > j + 1) v = mk(0.0, 0.0);
+      else if (h == a) continue;
+      h[r + (size_t)j * n] = v;
+    }
+}
+
+// ---- stage 4: shifted QR ------------------------------------------------------------------------
+struct HqrLaunch { int W, ns_max, steps_max; };
+SD_HD size_t hqr_smem_bytes(const HqrLaunch& q) {
+  size_t b = 160 * sizeof(double);
+  b += (size_t)q.W * (q.W + 1) * sizeof(cplx);
+  b += (size_t)q.steps_max * q.ns_max * sizeof(Refl);
+  b += (size_t)q.ns_max * sizeof(Refl);
+  b += (size_t)q.ns_max * sizeof(cplx);
+  b += (size_t)q.ns_max * (q.ns_max + 1) * sizeof(cplx);
+  b += sizeof(SmallCtl);
+  return b;
+}
+
+__global__ void k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* sp = smem_raw;
+  double* red = reinterpret_cast<double*>(sp); sp += 160 * sizeof(double);
+  HqrSmem sh;
+  sh.W = q.W; sh.ldw = q.W + 1; sh.ns_max = q.ns_max; sh.steps_max = q.steps_max;
+  sh.win = reinterpret_cast<cplx*>(sp); sp += (size_t)q.W * (q.W + 1) * sizeof(cplx);
+  sh.rec = reinterpret_cast<Refl*>(sp); sp += (size_t)q.steps_max * q.ns_max * sizeof(Refl);
+  sh.cur = reinterpret_cast<Refl*>(sp); sp += (size_t)q.ns_max * sizeof(Refl);
+  sh.shifts = reinterpret_cast<cplx*>(sp); sp += (size_t)q.ns_max * sizeof(cplx);
+  sh.sm = reinterpret_cast<cplx*>(sp); sp += (size_t)q.ns_max * (q.ns_max + 1) * sizeof(cplx);
+  sh.ctl = reinterpret_cast<SmallCtl*>(sp);
+  Cta c = make_cta(red);
+  const int p = blockIdx.x;
+  int r = cta_hqr(c, sh, Hq + (size_t)p * hstride, n, n, ilohi[2 * p], ilohi[2 * p + 1], w + (size_t)p * n);
+  if (threadIdx.x == 0) info[p] = r;
+}
+
+// ---- stage 5: sort (stable, ascending imaginary part) --------------------------------------------
+// mode 1 (temporal): key = Im(w).  mode 2 (spatial): alpha = 1/lambda (0 if lambda == 0), key = Im(alpha)
+// (spatial.f90:1065-1084).  mode 0: no sort (generic solver).
+// out: sorted eigenvalue (omega or alpha); lam: the matrix eigenvalue in the same order, perturbed
+// like ZHSEIN does for (nearly) coincident values so inverse iteration yields independent vectors.
+__global__ void k_sort(const cplx* w, int n, int mode, const double* hnorm, cplx* out, cplx* lam) {
+  const int p = blockIdx.x;
+  const cplx* wp = w + (size_t)p * n;
+  cplx* op = out + (size_t)p * n;
+  cplx* lp = lam + (size_t)p * n;
+  const double eps3 = fmax(SD_ULP * hnorm[p], SD_SAFMIN * ((double)n / SD_ULP));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    cplx wi = wp[i];
+    cplx vi = wi;
+    if (mode == 2) vi = is_zero(wi) ? mk(0.0, 0.0) : cdiv(mk(1.0, 0.0), wi);
+    int rank = i;
+    if (mode != 0) {
+      rank = 0;
+      const double key = vi.im;
+      for (int j = 0; j < n; ++j) {
+        cplx wj = wp[j];
+        double kj = wj.im;
+        if (mode == 2) kj = is_zero(wj) ? 0.0 : cdiv(mk(1.0, 0.0), wj).im;
+        if (kj < key || (kj == key && j < i)) ++rank;
+      }
+    }
+    int close = 0;   // earlier (in input order) eigenvalues closer than eps3
+    for (int j = 0; j < i; ++j) if (cabs1(wp[j] - wi) < eps3) ++close;
+    op[rank] = vi;
+    lp[rank] = wi + mk(eps3 * close, 0.0);
+  }
+}
+
+// ---- stage 6: eigenvectors ----------------------------------------------------------------------
+// grid (chunks, batch); each warp takes eigen-indices e = chunk*warps + wid, += chunks*warps
+__global__ void k_evec(const cplx* Hh, size_t hstride, int n, const int* ilohi, const cplx* tau, const double* scale,
+                       const cplx* lam, const double* hnorm, int scale_rows, cplx* V, size_t vstride, int* vinfo) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta w = make_cta(nullptr);
+  const int p = blockIdx.y;
+  cplx* cvec = reinterpret_cast<cplx*>(smem_raw) + (size_t)w.wid * 2 * n;
+  cplx* yvec = cvec + n;
+  unsigned char* flag = smem_raw + (size_t)w.nw * 2 * n * sizeof(cplx) + (size_t)w.wid * n;
+  const int ilo = ilohi[2 * p], ihi = ilohi[2 * p + 1];
+  int bad = 0;
+  for (int e = blockIdx.x * w.nw + w.wid; e < n; e += gridDim.x * w.nw) {
+    bad += warp_eigvec(w, Hh + (size_t)p * hstride, n, n, ilo, ihi, tau + (size_t)p * n, scale + (size_t)p * n,
+                       lam[(size_t)p * n + e], hnorm[p], scale_rows, cvec, yvec, flag, V + (size_t)p * vstride + (size_t)e * n);
+  }
+  if (bad && w.lane == 0) atomicAdd(vinfo + p, bad);
+}
+
+}  // namespace stab

@@ -1,0 +1,529 @@
+// stabgpu.cu -- C-ABI implementation (include/stabgpu.h): device-memory plans, stage launches,
+// host<->device staging.  No CPU fallback: every compute entry point requires a CUDA device.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/stabgpu.h"
+#include "kernels.cuh"
+
+using namespace stab;
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1;
+bool g_inited = false;
+struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; } g_tune;
+
+int fail(const std::string& m) { g_err = m; return 1; }
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"; \
+      return 1;                                                                                    \
+    }                                                                                              \
+  } while (0)
+
+int ensure_init() {
+  if (g_inited) return 0;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("libstabgpu: no CUDA device available (there is no CPU fallback for the hot path)");
+  if (g_device < 0) {
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    g_device = cur;
+  }
+  if (g_device >= ndev) return fail("libstabgpu: device index out of range");
+  CU(cudaSetDevice(g_device));
+  g_inited = true;
+  return 0;
+}
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    if (count == 0) return 0;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) { p = nullptr; g_err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e); return 1; }
+    n = count;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DBuf() { release(); }
+};
+
+Phys phys_from(const stabgpu_params* p) {
+  Phys q;
+  q.Ma = p->Ma; q.Re = p->Re; q.Pr = p->Pr; q.gamma = p->gamma; q.gamma1 = p->gamma1; q.cp = p->cp;
+  q.Te = p->Te; q.rmue = p->rmue; q.rlme = p->rlme; q.cone = p->cone;
+  for (int k = 0; k < 3; ++k) q.datmat[k] = p->datmat[k];
+  q.mattyp = p->mattyp;
+  q.navier = !(p->Re >= 1.0e98 || p->Re == 0.0);
+  return q;
+}
+
+enum Stage { ST_ASM = 0, ST_LU, ST_BAL, ST_HESS, ST_PREP, ST_QR, ST_SORT, ST_EVEC, ST_N };
+
+}  // namespace
+
+struct stabgpu_plan {
+  int kind = 0;            // 1 temporal, 2 spatial, 3 generic matrices
+  stabgpu_params prm;
+  int ny = 0, n = 0, N = 0; // n = 5 ny, N = order of the eigenproblem (n or 2n)
+  int cap = 0, npts = 0;
+  int want_vectors = 0;
+  cudaStream_t stream = nullptr;
+  // grid / profile
+  DBuf<double> vm, g2, g22, deta, d2eta, D1, D2, Dt2w, h5;
+  bool has_h5 = false;
+  // sweep values
+  DBuf<cplx> s1, s2;
+  DBuf<double> Re, Ma;
+  bool has_Re = false, has_Ma = false;
+  // work
+  DBuf<cplx> coef, A, C, Hq, V, tau, w, eig, lam;
+  DBuf<double> scale, hnorm;
+  DBuf<int> cnt, ilohi, info_lu, info_qr, info_v;
+  cudaEvent_t ev[ST_N + 1] = {};
+  float ms[ST_N] = {};
+  long long launches = 0;
+  GridDev grid() const {
+    GridDev g;
+    g.ny = ny; g.wallt = prm.wallt; g.top = prm.top;
+    g.D1 = D1.p; g.D2 = D2.p; g.Dt2w = Dt2w.p; g.deta = deta.p; g.d2eta = d2eta.p;
+    g.vm = vm.p; g.g2vm = g2.p; g.g22vm = g22.p; g.h5 = has_h5 ? h5.p : nullptr;
+    return g;
+  }
+};
+
+namespace {
+
+size_t per_point_bytes(int kind, int n, int N, int ny, int want_vectors) {
+  size_t b = 0;
+  b += (size_t)N * N * 16;                           // A (operand of the eigensolve)
+  if (kind == 2) b += (size_t)n * n * 16;            // C0
+  if (want_vectors) b += 2 * (size_t)N * N * 16;     // Hq + V
+  b += (size_t)ny * 150 * 16;                        // coefficients
+  b += (size_t)N * (16 * 4 + 8 + 4) + 64;
+  return b;
+}
+
+int plan_alloc(stabgpu_plan* pl, int max_pts) {
+  size_t freeb = 0, totalb = 0;
+  CU(cudaMemGetInfo(&freeb, &totalb));
+  size_t ppb = per_point_bytes(pl->kind, pl->n, pl->N, pl->ny, pl->want_vectors);
+  size_t capmem = (size_t)(0.85 * (double)freeb) / ppb;
+  int cap = max_pts;
+  if ((size_t)cap > capmem) cap = (int)capmem;
+  if (cap > 65535) cap = 65535;
+  if (cap < 1) return fail("libstabgpu: not enough device memory for a single point");
+  pl->cap = cap;
+  const int N = pl->N, n = pl->n, ny = pl->ny;
+  if (pl->s1.alloc(cap) || pl->s2.alloc(cap) || pl->Re.alloc(cap) || pl->Ma.alloc(cap)) return 1;
+  if (pl->kind != 3 && pl->coef.alloc((size_t)cap * ny * (pl->kind == 1 ? 75 : 150))) return 1;
+  if (pl->A.alloc((size_t)cap * N * N)) return 1;
+  if (pl->kind == 2 && pl->C.alloc((size_t)cap * n * n)) return 1;
+  if (pl->want_vectors && (pl->Hq.alloc((size_t)cap * N * N) || pl->V.alloc((size_t)cap * N * N))) return 1;
+  if (pl->tau.alloc((size_t)cap * N) || pl->w.alloc((size_t)cap * N) || pl->eig.alloc((size_t)cap * N) || pl->lam.alloc((size_t)cap * N)) return 1;
+  if (pl->scale.alloc((size_t)cap * N) || pl->hnorm.alloc(cap) || pl->cnt.alloc((size_t)cap * N)) return 1;
+  if (pl->ilohi.alloc(2 * (size_t)cap) || pl->info_lu.alloc(cap) || pl->info_qr.alloc(cap) || pl->info_v.alloc(cap)) return 1;
+  CU(cudaStreamCreate(&pl->stream));
+  for (int i = 0; i <= ST_N; ++i) CU(cudaEventCreate(&pl->ev[i]));
+  return 0;
+}
+
+// the eigen-pipeline on pl->A (npts matrices of order N): balance -> Hessenberg -> QR -> sort [-> vectors]
+int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
+  const int N = pl->N, np = pl->npts;
+  const size_t st = (size_t)N * N;
+  cudaStream_t s = pl->stream;
+  k_balance<<<np, 256, 0, s>>>(pl->A.p, st, N, pl->scale.p, pl->cnt.p, pl->ilohi.p);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(pl->ev[ST_BAL + 1], s));
+  {
+    size_t sm = 160 * sizeof(double) + 2 * (size_t)N * sizeof(cplx);
+    CU(cudaFuncSetAttribute(k_hessenberg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_hessenberg<<<np, g_tune.hess_threads, sm, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(pl->ev[ST_HESS + 1], s));
+  cplx* Hq = pl->want_vectors ? pl->Hq.p : pl->A.p;
+  k_prep_qr<<<np, 256, 0, s>>>(pl->A.p, st, Hq, st, N, pl->hnorm.p);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(pl->ev[ST_PREP + 1], s));
+  {
+    HqrLaunch q; q.W = g_tune.W; q.ns_max = g_tune.ns; q.steps_max = 64;
+    if (q.W - 2 < 2 * q.ns_max - 1 || q.steps_max < 2 * q.ns_max - 1 || q.W - 2 * q.ns_max - 1 < 4)
+      return fail("libstabgpu: invalid QR tuning (window too small for the shift count)");
+    size_t sm = hqr_smem_bytes(q);
+    CU(cudaFuncSetAttribute(k_hqr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_hqr<<<np, g_tune.qr_threads, sm, s>>>(Hq, st, N, pl->ilohi.p, pl->w.p, pl->info_qr.p, q);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(pl->ev[ST_QR + 1], s));
+  k_sort<<<np, 256, 0, s>>>(pl->w.p, N, sort_mode, pl->hnorm.p, pl->eig.p, pl->lam.p);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(pl->ev[ST_SORT + 1], s));
+  pl->launches += 5;
+  if (pl->want_vectors) {
+    CU(cudaMemsetAsync(pl->info_v.p, 0, sizeof(int) * np, s));
+    int warps = 8;
+    const size_t per_warp = 2 * (size_t)N * sizeof(cplx) + (size_t)N;
+    while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+    size_t sm = warps * per_warp;
+    if (sm > 227 * 1024) return fail("libstabgpu: matrix too large for the eigenvector kernel");
+    CU(cudaFuncSetAttribute(k_evec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int chunks = 1;
+    while (chunks * np < 2 * 148 && chunks * warps < N) chunks *= 2;
+    dim3 grid(chunks, np);
+    // the reflectors live in A (ZGEHRD layout); the QR ran on the copy Hq
+    k_evec<<<grid, warps * 32, sm, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->scale.p, pl->lam.p, pl->hnorm.p,
+                                        scale_rows, pl->V.p, st, pl->info_v.p);
+    CU(cudaGetLastError());
+    pl->launches += 1;
+  }
+  CU(cudaEventRecord(pl->ev[ST_EVEC + 1], s));
+  return 0;
+}
+
+int upload_grid(stabgpu_plan* pl, const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                const double* deta, const double* d2eta, const double* h5) {
+  const int ny = p->ny;
+  std::vector<double> D1((size_t)ny * ny), D2((size_t)ny * ny), Dt2w(ny), g2((size_t)ny * 5), g22((size_t)ny * 5);
+  stabgpu_mean_gradients(ny, p->wallt, vm, deta, d2eta, D1.data(), D2.data(), Dt2w.data(), g2.data(), g22.data());
+  if (!p->ider) {                                    // getmean2 path: analytic derivatives supplied (temporal.f90:99-103)
+    if (!g2vm || !g22vm) return fail("libstabgpu: ider=0 requires g2vm and g22vm");
+    std::memcpy(g2.data(), g2vm, sizeof(double) * ny * 5);
+    std::memcpy(g22.data(), g22vm, sizeof(double) * ny * 5);
+  }
+  if (pl->vm.alloc((size_t)ny * 5) || pl->g2.alloc((size_t)ny * 5) || pl->g22.alloc((size_t)ny * 5) || pl->deta.alloc(ny) ||
+      pl->d2eta.alloc(ny) || pl->D1.alloc((size_t)ny * ny) || pl->D2.alloc((size_t)ny * ny) || pl->Dt2w.alloc(ny))
+    return 1;
+  CU(cudaMemcpy(pl->vm.p, vm, sizeof(double) * ny * 5, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pl->g2.p, g2.data(), sizeof(double) * ny * 5, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pl->g22.p, g22.data(), sizeof(double) * ny * 5, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pl->deta.p, deta, sizeof(double) * ny, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pl->d2eta.p, d2eta, sizeof(double) * ny, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pl->D1.p, D1.data(), sizeof(double) * ny * ny, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pl->D2.p, D2.data(), sizeof(double) * ny * ny, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pl->Dt2w.p, Dt2w.data(), sizeof(double) * ny, cudaMemcpyHostToDevice));
+  pl->has_h5 = false;
+  if (h5) {
+    if (pl->h5.alloc((size_t)ny * 5)) return 1;
+    CU(cudaMemcpy(pl->h5.p, h5, sizeof(double) * ny * 5, cudaMemcpyHostToDevice));
+    pl->has_h5 = true;
+  }
+  return 0;
+}
+
+int check_params(const stabgpu_params* p) {
+  if (!p) return fail("libstabgpu: null params");
+  if (p->ny < 4 || p->ny > 512) return fail("libstabgpu: ny out of range [4,512]");
+  if (p->wallt != 0 && p->wallt != 2) return fail("Illegal value of wallt");   // temporal.f90:659-661
+  if (p->mattyp != 0 && p->mattyp != 1) return fail("libstabgpu: mattyp must be 0 or 1");
+  if (p->curve == 1) return fail("libstabgpu: curve=1 (calch) is out of scope; supply metrics through h5");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* stabgpu_last_error(void) { return g_err.c_str(); }
+
+int stabgpu_init(int device) {
+  g_inited = false;
+  g_device = device;
+  return ensure_init();
+}
+
+int stabgpu_finalize(void) {
+  if (g_inited) cudaDeviceSynchronize();
+  g_inited = false;
+  return 0;
+}
+
+int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb) {
+  if (ensure_init()) return 1;
+  cudaDeviceProp pr;
+  CU(cudaGetDeviceProperties(&pr, g_device));
+  if (name && name_len > 0) { std::strncpy(name, pr.name, name_len - 1); name[name_len - 1] = 0; }
+  if (sm_count) *sm_count = pr.multiProcessorCount;
+  if (mem_gb) *mem_gb = (double)pr.totalGlobalMem / 1.0e9;
+  return 0;
+}
+
+int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads) {
+  if (qr_window > 0) g_tune.W = qr_window;
+  if (qr_shifts > 0) g_tune.ns = qr_shifts;
+  if (qr_threads > 0) g_tune.qr_threads = qr_threads;
+  if (hess_threads > 0) g_tune.hess_threads = hess_threads;
+  return 0;
+}
+
+int stabgpu_plan_create(stabgpu_plan** out, int kind, const stabgpu_params* p, const double* vm, const double* g2vm,
+                        const double* g22vm, const double* deta, const double* d2eta, const double* h5, int max_pts,
+                        int want_vectors) {
+  if (ensure_init()) return 1;
+  if (kind != 1 && kind != 2) return fail("libstabgpu: plan kind must be 1 (temporal) or 2 (spatial)");
+  if (check_params(p)) return 1;
+  if (!vm || !deta || !d2eta || max_pts < 1) return fail("libstabgpu: bad argument");
+  stabgpu_plan* pl = new stabgpu_plan();
+  pl->kind = kind; pl->prm = *p; pl->ny = p->ny; pl->n = 5 * p->ny; pl->N = (kind == 1 ? 1 : 2) * pl->n;
+  pl->want_vectors = want_vectors ? 1 : 0;
+  if (upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, h5) || plan_alloc(pl, max_pts)) { delete pl; return 1; }
+  *out = pl;
+  return 0;
+}
+
+int stabgpu_plan_upload(stabgpu_plan* pl, int npts, const double* s1, const double* s2, const double* Re_pt, const double* Ma_pt) {
+  if (!pl || npts < 1 || npts > pl->cap || !s1 || !s2) return fail("libstabgpu: plan_upload bad argument");
+  pl->npts = npts;
+  CU(cudaMemcpyAsync(pl->s1.p, s1, sizeof(cplx) * npts, cudaMemcpyHostToDevice, pl->stream));
+  CU(cudaMemcpyAsync(pl->s2.p, s2, sizeof(cplx) * npts, cudaMemcpyHostToDevice, pl->stream));
+  pl->has_Re = Re_pt != nullptr; pl->has_Ma = Ma_pt != nullptr;
+  if (Re_pt) CU(cudaMemcpyAsync(pl->Re.p, Re_pt, sizeof(double) * npts, cudaMemcpyHostToDevice, pl->stream));
+  if (Ma_pt) CU(cudaMemcpyAsync(pl->Ma.p, Ma_pt, sizeof(double) * npts, cudaMemcpyHostToDevice, pl->stream));
+  CU(cudaStreamSynchronize(pl->stream));
+  return 0;
+}
+
+int stabgpu_plan_execute(stabgpu_plan* pl) {
+  if (!pl || pl->npts < 1) return fail("libstabgpu: plan_execute without uploaded points");
+  const int np = pl->npts, ny = pl->ny, n = pl->n, N = pl->N;
+  cudaStream_t s = pl->stream;
+  pl->launches = 0;
+  GridDev g = pl->grid();
+  Phys ph = phys_from(&pl->prm);
+  SweepDev sw; sw.s1 = pl->s1.p; sw.s2 = pl->s2.p; sw.Re = pl->has_Re ? pl->Re.p : nullptr; sw.Ma = pl->has_Ma ? pl->Ma.p : nullptr;
+  CU(cudaEventRecord(pl->ev[0], s));
+  dim3 cgrid((ny + 63) / 64, np);
+  dim3 agrid((n + ASM_ROWS - 1) / ASM_ROWS, (ny + ASM_JT - 1) / ASM_JT, np);
+  if (pl->kind == 1) {
+    k_node_coef_temporal<<<cgrid, 64, 0, s>>>(g, ph, sw, 0, 1, pl->coef.p, nullptr);
+    CU(cudaGetLastError());
+    k_assemble_temporal<<<agrid, ASM_ROWS, 0, s>>>(g, pl->coef.p, pl->A.p, (size_t)N * N);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(pl->ev[ST_ASM + 1], s));
+    CU(cudaEventRecord(pl->ev[ST_LU + 1], s));
+    CU(cudaMemsetAsync(pl->info_lu.p, 0, sizeof(int) * np, s));
+    pl->launches += 2;
+    if (run_eigen(pl, 1, n)) return 1;
+  } else {
+    k_node_coef_spatial<<<cgrid, 64, 0, s>>>(g, ph, sw, 0, pl->coef.p);
+    CU(cudaGetLastError());
+    k_assemble_spatial<<<agrid, ASM_ROWS, 0, s>>>(g, pl->coef.p, pl->C.p, (size_t)n * n, pl->A.p, (size_t)N * N);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(pl->ev[ST_ASM + 1], s));
+    size_t sm = 160 * sizeof(double) + (size_t)n * sizeof(cplx);
+    k_lu<<<np, 512, sm, s>>>(pl->C.p, (size_t)n * n, n, pl->A.p, (size_t)N * N, N, N, pl->info_lu.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(pl->ev[ST_LU + 1], s));
+    pl->launches += 3;
+    if (run_eigen(pl, 2, 0)) return 1;
+  }
+  CU(cudaStreamSynchronize(s));
+  for (int i = 0; i < ST_N; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, pl->ev[i], pl->ev[i + 1]);
+    pl->ms[i] = t;
+  }
+  return 0;
+}
+
+int stabgpu_plan_download(stabgpu_plan* pl, double* eig, double* evec, int* info) {
+  if (!pl || pl->npts < 1) return fail("libstabgpu: plan_download without results");
+  const int np = pl->npts, N = pl->N;
+  if (eig) CU(cudaMemcpy(eig, pl->eig.p, sizeof(cplx) * (size_t)np * N, cudaMemcpyDeviceToHost));
+  if (evec) {
+    if (!pl->want_vectors) return fail("libstabgpu: plan was created without eigenvectors");
+    CU(cudaMemcpy(evec, pl->V.p, sizeof(cplx) * (size_t)np * N * N, cudaMemcpyDeviceToHost));
+  }
+  if (info) {
+    std::vector<int> a(np), b(np);
+    CU(cudaMemcpy(a.data(), pl->info_lu.p, sizeof(int) * np, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(b.data(), pl->info_qr.p, sizeof(int) * np, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < np; ++i) info[i] = a[i] ? a[i] : b[i];
+  }
+  return 0;
+}
+
+int stabgpu_plan_stage_times(stabgpu_plan* pl, float* ms) {
+  if (!pl) return 1;
+  for (int i = 0; i < ST_N; ++i) ms[i] = pl->ms[i];
+  return 0;
+}
+
+long long stabgpu_plan_launch_count(stabgpu_plan* pl) { return pl ? pl->launches : 0; }
+
+int stabgpu_plan_destroy(stabgpu_plan* pl) {
+  if (!pl) return 0;
+  if (pl->stream) cudaStreamDestroy(pl->stream);
+  for (int i = 0; i <= ST_N; ++i) if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
+  delete pl;
+  return 0;
+}
+
+static int batch_common(int kind, const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                        const double* deta, const double* d2eta, const double* h5, int npts, const double* s1,
+                        const double* s2, const double* Re_pt, const double* Ma_pt, int want_vectors, double* eig,
+                        double* evec, int* info) {
+  if (npts < 1 || !s1 || !s2 || !eig) return fail("libstabgpu: bad argument");
+  if (want_vectors && !evec) return fail("libstabgpu: want_vectors set but evec is NULL");
+  stabgpu_plan* pl = nullptr;
+  if (stabgpu_plan_create(&pl, kind, p, vm, g2vm, g22vm, deta, d2eta, h5, npts, want_vectors)) return 1;
+  const int N = pl->N;
+  int rc = 0;
+  for (int p0 = 0; p0 < npts && !rc; p0 += pl->cap) {
+    int m = npts - p0; if (m > pl->cap) m = pl->cap;
+    rc = stabgpu_plan_upload(pl, m, s1 + 2 * (size_t)p0, s2 + 2 * (size_t)p0, Re_pt ? Re_pt + p0 : nullptr, Ma_pt ? Ma_pt + p0 : nullptr);
+    if (!rc) rc = stabgpu_plan_execute(pl);
+    if (!rc) rc = stabgpu_plan_download(pl, eig + 2 * (size_t)p0 * N, want_vectors ? evec + 2 * (size_t)p0 * N * N : nullptr,
+                                        info ? info + p0 : nullptr);
+  }
+  stabgpu_plan_destroy(pl);
+  return rc;
+}
+
+int stabgpu_temporal_batch(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                           const double* deta, const double* d2eta, int npts, const double* alpha, const double* beta,
+                           const double* Re_pt, const double* Ma_pt, int want_vectors, double* omg, double* evec, int* info) {
+  return batch_common(1, p, vm, g2vm, g22vm, deta, d2eta, nullptr, npts, alpha, beta, Re_pt, Ma_pt, want_vectors, omg, evec, info);
+}
+
+int stabgpu_spatial_batch(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                          const double* deta, const double* d2eta, const double* h5, int npts, const double* omega,
+                          const double* beta, const double* Re_pt, const double* Ma_pt, int want_vectors, double* alp,
+                          double* evec, int* info) {
+  return batch_common(2, p, vm, g2vm, g22vm, deta, d2eta, h5, npts, omega, beta, Re_pt, Ma_pt, want_vectors, alp, evec, info);
+}
+
+int stabgpu_zgeev_batch(int n, int batch, const double* A, int want_vectors, double* w, double* V, int* info) {
+  if (ensure_init()) return 1;
+  if (n < 2 || batch < 1 || !A || !w) return fail("libstabgpu: bad argument");
+  if (want_vectors && !V) return fail("libstabgpu: want_vectors set but V is NULL");
+  stabgpu_plan* pl = new stabgpu_plan();
+  pl->kind = 3; pl->ny = 0; pl->n = n; pl->N = n; pl->want_vectors = want_vectors ? 1 : 0;
+  int rc = plan_alloc(pl, batch);
+  for (int p0 = 0; p0 < batch && !rc; p0 += pl->cap) {
+    int m = batch - p0; if (m > pl->cap) m = pl->cap;
+    pl->npts = m;
+    const size_t st = (size_t)n * n;
+    rc = (cudaMemcpy(pl->A.p, A + 2 * (size_t)p0 * st, sizeof(cplx) * m * st, cudaMemcpyHostToDevice) != cudaSuccess);
+    if (rc) { fail("libstabgpu: H2D copy failed"); break; }
+    cudaEventRecord(pl->ev[0], pl->stream);
+    cudaEventRecord(pl->ev[ST_ASM + 1], pl->stream);
+    cudaEventRecord(pl->ev[ST_LU + 1], pl->stream);
+    pl->launches = 0;
+    rc = run_eigen(pl, 0, 0);
+    if (!rc) rc = (cudaStreamSynchronize(pl->stream) != cudaSuccess);
+    if (rc) { if (g_err.empty()) fail("libstabgpu: eigen pipeline failed"); break; }
+    cudaMemsetAsync(pl->info_lu.p, 0, sizeof(int) * m, pl->stream);
+    cudaStreamSynchronize(pl->stream);
+    rc = stabgpu_plan_download(pl, w + 2 * (size_t)p0 * n, want_vectors ? V + 2 * (size_t)p0 * st : nullptr, info ? info + p0 : nullptr);
+  }
+  {
+    cudaError_t e = cudaGetLastError();
+    if (!rc && e != cudaSuccess) rc = fail(std::string("libstabgpu: ") + cudaGetErrorString(e));
+  }
+  stabgpu_plan_destroy(pl);
+  return rc;
+}
+
+int stabgpu_debug_stages(int n, const double* A, double* balanced, double* scale, int* ilo, int* ihi, double* hess, double* tau) {
+  if (ensure_init()) return 1;
+  stabgpu_plan* pl = new stabgpu_plan();
+  pl->kind = 3; pl->n = n; pl->N = n; pl->want_vectors = 0;
+  int rc = plan_alloc(pl, 1);
+  if (rc) { stabgpu_plan_destroy(pl); return 1; }
+  const size_t st = (size_t)n * n;
+  cudaStream_t s = pl->stream;
+  cudaMemcpy(pl->A.p, A, sizeof(cplx) * st, cudaMemcpyHostToDevice);
+  k_balance<<<1, 256, 0, s>>>(pl->A.p, st, n, pl->scale.p, pl->cnt.p, pl->ilohi.p);
+  cudaStreamSynchronize(s);
+  int lh[2];
+  cudaMemcpy(lh, pl->ilohi.p, sizeof(lh), cudaMemcpyDeviceToHost);
+  if (ilo) *ilo = lh[0];
+  if (ihi) *ihi = lh[1];
+  if (balanced) cudaMemcpy(balanced, pl->A.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
+  if (scale) cudaMemcpy(scale, pl->scale.p, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  size_t sm = 160 * sizeof(double) + 2 * (size_t)n * sizeof(cplx);
+  cudaFuncSetAttribute(k_hessenberg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_hessenberg<<<1, g_tune.hess_threads, sm, s>>>(pl->A.p, st, n, pl->ilohi.p, pl->tau.p);
+  cudaStreamSynchronize(s);
+  if (hess) cudaMemcpy(hess, pl->A.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
+  if (tau) cudaMemcpy(tau, pl->tau.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaGetLastError();
+  stabgpu_plan_destroy(pl);
+  if (e != cudaSuccess) return fail(std::string("libstabgpu: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+static int inspect_common(int kind, const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                          const double* deta, const double* d2eta, const double* h5, const double* s1, const double* s2,
+                          double* o0, double* o1, double* o2) {
+  if (ensure_init()) return 1;
+  if (check_params(p)) return 1;
+  stabgpu_plan* pl = new stabgpu_plan();
+  pl->kind = kind; pl->prm = *p; pl->ny = p->ny; pl->n = 5 * p->ny; pl->N = pl->n; pl->want_vectors = 0;
+  int rc = upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, h5);
+  const int ny = p->ny, n = pl->n;
+  const size_t st = (size_t)n * n;
+  DBuf<cplx> coef, blk, m0, m1, m2, sv1, sv2;
+  if (!rc) rc = coef.alloc((size_t)ny * 150) || blk.alloc((size_t)ny * 25) || m0.alloc(st) || m1.alloc(st) || m2.alloc(st) || sv1.alloc(1) || sv2.alloc(1);
+  if (rc) { stabgpu_plan_destroy(pl); return 1; }
+  cudaMemcpy(sv1.p, s1, sizeof(cplx), cudaMemcpyHostToDevice);
+  cudaMemcpy(sv2.p, s2, sizeof(cplx), cudaMemcpyHostToDevice);
+  GridDev g = pl->grid();
+  Phys ph = phys_from(p);
+  SweepDev sw; sw.s1 = sv1.p; sw.s2 = sv2.p; sw.Re = nullptr; sw.Ma = nullptr;
+  dim3 cgrid((ny + 63) / 64, 1);
+  const int eb = (int)((st + 255) / 256);
+  if (kind == 1) {
+    k_node_coef_temporal<<<cgrid, 64>>>(g, ph, sw, 0, 0, coef.p, blk.p);
+    k_inspect_temporal<<<eb, 256>>>(g, coef.p, blk.p, m0.p, m1.p);
+  } else {
+    k_node_coef_spatial<<<cgrid, 64>>>(g, ph, sw, 0, coef.p);
+    k_inspect_spatial<<<eb, 256>>>(g, coef.p, m0.p, m1.p, m2.p);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) {
+    cudaMemcpy(o0, m0.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
+    cudaMemcpy(o1, m1.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
+    if (o2) cudaMemcpy(o2, m2.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
+    e = cudaGetLastError();
+  }
+  stabgpu_plan_destroy(pl);
+  if (e != cudaSuccess) return fail(std::string("libstabgpu: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int stabgpu_temporal_assemble(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                              const double* deta, const double* d2eta, const double* alpha, const double* beta,
+                              double* A0, double* B0) {
+  return inspect_common(1, p, vm, g2vm, g22vm, deta, d2eta, nullptr, alpha, beta, A0, B0, nullptr);
+}
+
+int stabgpu_spatial_assemble(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                             const double* deta, const double* d2eta, const double* h5, const double* omega,
+                             const double* beta, double* C0, double* C1, double* C2) {
+  return inspect_common(2, p, vm, g2vm, g22vm, deta, d2eta, h5, omega, beta, C0, C1, C2);
+}
+
+int stabgpu_temporal_polish(const stabgpu_params*, const double*, const double*, const double*, const double*, const double*,
+                            const double*, const double*, const double*, const double*, int, double, double*, double*,
+                            double*, int*) {
+  return fail("libstabgpu: stabgpu_temporal_polish is not implemented yet");
+}
+
+}  // extern "C"
