@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- full-spectrum eigensolves/sec on the TS temporal alpha-sweep at Ny=128 (BASELINE.json
+configs[1]), one process per GPU.
+
+A "step" is one pass of the hot path (assembly -> B0^-1 A0 -> balance -> Hessenberg -> QR ->
+sort [-> eigenvectors]) over this rank's shard of the sweep.  `value` is device-resident
+throughput (sweep values already in HBM); `e2e` is the same metric through the reference-facing
+C-ABI call `stabgpu_temporal_batch` with pinned HOST buffers, H2D/D2H inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--ny 128] [--no-vectors]
+  python bench.py --impl reference ...     # the reference's CPU arithmetic (oracle port) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--points", type=int, default=256, help="sweep points per GPU per step (weak scaling)")
+    ap.add_argument("--ny", type=int, default=128)
+    ap.add_argument("--no-vectors", action="store_true", help="eigenvalues only (the reference always computes vectors)")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="points in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---- workload: TStest profile, thesis TS deck, alpha sweep (mtemporal enumeration) ---------------
+def workload(ny, npts_total):
+    """Returns (case, alpha[npts_total], beta[npts_total]).  alpha in [0.05, 0.45)."""
+    import stab_b200 as sb
+    deck = open(os.path.join(ROOT, "tests", "golden", "ts_temporal_ny96.inp")).read()
+    c = sb.read_deck(deck)
+    c.params.ny = ny
+    c.load_profile(os.path.join(ROOT, "tests", "golden", "ts_profile.0"))
+    a, b = sb.mtemporal_points(0.05, 0.45, 0.4 / npts_total, 0.0, 0.1, 1.0)
+    assert a.size == npts_total, (a.size, npts_total)
+    return c, a + 0j, b + 0j
+
+
+# ---- CPU arm: the reference's arithmetic (oracle port: scipy-LAPACK zgesv + zgeev) ---------------
+def _cpu_worker(args):
+    ny, alphas, as_coded, want_vectors = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    import stab_oracle as so
+    deck = open(os.path.join(ROOT, "tests", "golden", "ts_temporal_ny96.inp")).read()
+    p = so.read_deck(deck)
+    p.ny = ny
+    p.finish()
+    g = so.prepare(p, open(os.path.join(ROOT, "tests", "golden", "ts_profile.0")).read())
+    t0 = time.perf_counter()
+    out = []
+    for a in alphas:
+        p.alpha = complex(a)
+        r = so.solve_temporal(p, g["vm"], g["deta"], g["d2eta"], want_vectors=want_vectors, as_coded=as_coded)
+        out.append(r["omg"][:4])
+    return time.perf_counter() - t0, len(out)
+
+
+def cpu_arm(ny, alphas, want_vectors, cores=None):
+    """One worker per core, one BLAS thread each (the natural CPU parallelisation of a sweep of
+    independent points).  Returns (solves/s, cores, wall seconds)."""
+    import multiprocessing as mp
+    cores = cores or len(os.sched_getaffinity(0))
+    cores = max(1, min(cores, len(alphas)))
+    chunks = [list(alphas[i::cores]) for i in range(cores)]
+    ctx = mp.get_context("spawn")
+    best = None
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(16, [0.3], False, want_vectors)] * cores)        # import + warm-up
+        for as_coded in (False, True):       # optimal workspace vs the reference's lwork=2n: quote the faster
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(ny, ch, as_coded, want_vectors) for ch in chunks])
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, as_coded)
+    return len(alphas) / best[0], cores, best[0], best[1]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    sample = args.cpu_sample or min(args.points, max(cores, 8))
+    alphas = np.linspace(0.05, 0.45, sample, endpoint=False)
+    want_vectors = not args.no_vectors
+    times = []
+    for it in range(args.warmup + args.steps):
+        rate, used, dt, as_coded = cpu_arm(args.ny, alphas, want_vectors)
+        if it >= args.warmup:
+            times.append(dt)
+        if it == 0 and dt > 60:           # keep the whole run bounded
+            times = [dt]
+            break
+    ms = 1e3 * float(np.mean(times))
+    val = sample / (ms / 1e3)
+    desc = f"{sample} of the sweep's points per step, one worker per core ({used}), 1 BLAS thread each"
+    line = {
+        "impl": "reference", "metric": "full-spectrum eigensolves/sec at Ny=%d" % args.ny, "value": val,
+        "unit": "eigensolves/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+        "config": config_dict(args, sample),
+        "cpu_baseline": {"value": val, "unit": "eigensolves/s", "cores": used, "kind": "port", "sample": desc,
+                         "lapack": "scipy OpenBLAS zgesv+zgeev('N','%s'), %s workspace" % ("V" if want_vectors else "N", "lwork=2n (as coded)" if as_coded else "optimal")},
+        "e2e": {"value": val, "unit": "eigensolves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def config_dict(args, npts):
+    return {"workload": "TStest Tollmien-Schlichting temporal alpha-sweep at fixed Re (BASELINE configs[1]; SURVEY C2): "
+                        "TStest/profile.0, M=0.3 Re=1000 Pr=1, Yi=1 algebraic map, alpha in [0.05,0.45), beta=0",
+            "ny": args.ny, "n": 5 * args.ny, "points_per_gpu_per_step": npts,
+            "eigenvectors": not args.no_vectors,
+            "l2": "per-step working set (points x 16 n^2 B >= 1.6 GB) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ---- clocks sampler -------------------------------------------------------------------------------
+class Clocks:
+    def __init__(self, dev):
+        self.dev, self.rows, self.stop = dev, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([s.strip() for s in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(r[6]) for r in self.rows)}
+
+
+class DevArray:
+    """__cuda_array_interface__ wrapper of a raw device pointer (for torch.as_tensor)."""
+
+    def __init__(self, ptr, nfloat64):
+        self.__cuda_array_interface__ = {"shape": (nfloat64,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def fp64_gemm_peak(torch, dev):
+    """cuBLAS DGEMM 4096^3 burst TFLOP/s -- MEASURED_PEAKS.json has no FP64 entry."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        a @ b
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+        best = max(best, 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b
+    return best
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import stab_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the stab hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sb.init(local)
+
+    want_vectors = not args.no_vectors
+    P = args.points
+    case, alpha_all, beta_all = workload(args.ny, P * world)
+    lo, hi = sb.shard_range(P * world, rank, world)
+    alpha, beta = alpha_all[lo:hi], beta_all[lo:hi]
+    n = 5 * args.ny
+    prm = case.params
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    plan = sb.Plan(1, prm, case.vm, case.deta, case.d2eta, P, want_vectors=want_vectors)
+    if plan.capacity < P:
+        raise SystemExit(f"bench.py: {P} points do not fit the device workspace (capacity {plan.capacity})")
+    plan.upload(alpha, beta)
+    stream = torch.cuda.ExternalStream(plan.stream(), device=dev)
+    eig_dev = torch.as_tensor(DevArray(plan.eig_dev(), 2 * n * P), device=dev)
+    gathered = torch.empty(world * eig_dev.numel(), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        plan.execute()
+        if dist is not None:                        # the final result gather of the sweep
+            dist.all_gather_into_tensor(gathered, eig_dev)
+
+    for _ in range(args.warmup):
+        step()
+    stage_acc = {}
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with Clocks(local) as clk:
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+            for k, v in plan.stage_times().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    # the gather (N > 1) runs on torch's stream after execute() has synchronised: wall covers it, events cover the kernels
+    ms_total = max(dev_ms, 1e3 * wall) if world > 1 else dev_ms
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = P * world / (ms_step * 1e-3)
+    launches = plan.launch_count() * args.steps
+    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    plan_info = np.zeros(P, dtype=np.int32)
+    sb.lib().stabgpu_plan_download(plan._h, None, None, plan_info.ctypes.data)
+    n_fail = int(np.count_nonzero(plan_info))
+
+    # ---- e2e arm: the C-ABI batch call with pinned host buffers ----------------------------------
+    omg_h = torch.empty((P, n), dtype=torch.complex128, pin_memory=True).numpy()
+    ev_h = torch.empty((P, n, n), dtype=torch.complex128, pin_memory=True).numpy() if want_vectors else None
+    info_h = torch.empty((P,), dtype=torch.int32, pin_memory=True).numpy()
+    al_h = torch.empty((P,), dtype=torch.complex128, pin_memory=True).numpy(); al_h[:] = alpha
+    be_h = torch.empty((P,), dtype=torch.complex128, pin_memory=True).numpy(); be_h[:] = beta
+    plan.destroy()
+    del eig_dev
+
+    def e2e_step():
+        sb.temporal_batch(prm, case.vm, case.deta, case.d2eta, al_h, be_h, want_vectors=want_vectors, out=(omg_h, ev_h, info_h))
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = P * world * args.steps / float(t.item())
+    ny = args.ny
+    h2d = 2 * 16 * P + 8 * (ny * 5 * 3 + 3 * ny + 2 * ny * ny)
+    d2h = 16 * n * P + (16 * n * n * P if want_vectors else 0) + 4 * P
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the graded kernel (Hessenberg stage) + measured FP64 peak --------------------
+    peak = fp64_gemm_peak(torch, dev)
+    hess_flops = (40.0 / 3.0) * n ** 3 * P
+    hess_ms = stage_ms.get("hessenberg", 0.0)
+    achieved = hess_flops / (hess_ms * 1e-3) / 1e12 if hess_ms > 0 else 0.0
+    total_stage = sum(stage_ms.values()) or 1.0
+    roofline = {"kernel": "k_hessenberg (stage 3, the graded stage of the north star)", "bound": "tensor",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": None, "flops_per_launch": hess_flops,
+                "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 burst via torch.matmul (MEASURED_PEAKS.json has no FP64 entry)",
+                "kernel_share_of_step": hess_ms / total_stage}
+    asm_ms = stage_ms.get("assemble", 0.0)
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm_peak = 6650.0
+    asm_gbs = 16.0 * n * n * P / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0
+
+    line = {
+        "metric": "full-spectrum eigensolves/sec at Ny=%d" % ny, "value": value, "unit": "eigensolves/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+        "config": config_dict(args, P),
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_val, "unit": "eigensolves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "stabgpu_temporal_batch, pinned host buffers"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "stages_ms_per_step": stage_ms,
+        "assembly_roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": asm_gbs / hbm_peak if hbm_peak else None},
+        "failed_points": n_fail,
+    }
+    if not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        sample = args.cpu_sample or min(P, max(cores, 8))
+        rate, used, dt, as_coded = cpu_arm(ny, np.linspace(0.05, 0.45, sample, endpoint=False), want_vectors)
+        line["cpu_baseline"] = {"value": rate, "unit": "eigensolves/s", "cores": used, "kind": "port",
+                                "sample": f"{sample} points of the same sweep, one worker per core, 1 BLAS thread each, "
+                                          f"{'lwork=2n' if as_coded else 'optimal workspace'} (faster of the two), {dt:.1f} s"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -127,6 +127,9 @@ int stabgpu_plan_execute(stabgpu_plan* plan);                                   
 int stabgpu_plan_download(stabgpu_plan* plan, double* eig, double* evec, int* info); /* D2H */
 int stabgpu_plan_stage_times(stabgpu_plan* plan, float* ms /* 8 floats */);      /* CUDA-event time per stage of the last execute */
 long long stabgpu_plan_launch_count(stabgpu_plan* plan);                         /* kernels launched by the last execute */
+void* stabgpu_plan_stream(stabgpu_plan* plan);                                   /* the cudaStream_t the plan launches on (for external CUDA-event timing) */
+void* stabgpu_plan_eig_dev(stabgpu_plan* plan);                                  /* DEVICE pointer: sorted eigenvalues, N x npts complex (for the multi-GPU result gather) */
+int stabgpu_plan_capacity(stabgpu_plan* plan);                                   /* points per wave that fit the device workspace */
 int stabgpu_plan_destroy(stabgpu_plan* plan);
 
 /* ---- sweep drivers and file formats (host) ------------------------------------------------------ */

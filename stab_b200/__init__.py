@@ -17,6 +17,7 @@ from .binding import (  # noqa: F401
     device_info,
     edge_properties,
     getmean,
+    init,
     lib,
     mean_gradients,
     mspatial_points,

@@ -1,0 +1,409 @@
+"""ctypes binding over libstabgpu.so (include/stabgpu.h).
+
+Only plain pointers and sizes cross the boundary; numpy arrays are passed as host pointers.
+There is no CPU fallback: a missing library raises at import of the first symbol, a missing CUDA
+device makes every compute entry point raise `StabGpuError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstabgpu.so")
+NDOF = 5
+
+
+class StabGpuError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """struct stabgpu_params: the scalar run state of module stuff (stuff.f90:11-59)."""
+
+    _fields_ = [
+        ("ny", C.c_int), ("mattyp", C.c_int), ("wallt", C.c_int), ("top", C.c_int), ("curve", C.c_int),
+        ("ider", C.c_int), ("ievec", C.c_int), ("wall", C.c_int),
+        ("Ma", C.c_double), ("Re", C.c_double), ("Pr", C.c_double),
+        ("gamma", C.c_double), ("gamma1", C.c_double), ("cp", C.c_double),
+        ("Te", C.c_double), ("rmue", C.c_double), ("rlme", C.c_double), ("cone", C.c_double),
+        ("datmat", C.c_double * 3),
+        ("yi", C.c_double), ("ymax", C.c_double), ("x", C.c_double),
+    ]
+
+    @classmethod
+    def default(cls) -> "Params":
+        p = cls()
+        lib().stabgpu_params_default(C.byref(p))
+        return p
+
+    def copy(self) -> "Params":
+        q = Params()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(Params))
+        return q
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_pp = C.POINTER(Params)
+
+
+def lib():
+    """Load libstabgpu.so (once) and declare the prototypes of include/stabgpu.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise StabGpuError(
+            f"{LIB_PATH} not found: build it with `make -C stab_b200/csrc` or __graft_entry__.build() "
+            "(there is no CPU fallback for the stab hot path)")
+    L = C.CDLL(LIB_PATH)
+
+    def proto(name, res, args):
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+
+    i, d, vp, cp = C.c_int, C.c_double, C.c_void_p, C.c_char_p
+    proto("stabgpu_init", i, [i])
+    proto("stabgpu_finalize", i, [])
+    proto("stabgpu_last_error", cp, [])
+    proto("stabgpu_device_info", i, [cp, i, _ip, _dp])
+    proto("stabgpu_set_tuning", i, [i, i, i, i])
+    proto("stabgpu_params_default", None, [_pp])
+    proto("stabgpu_edge_properties", i, [_pp, d])
+    proto("stabgpu_sgengrid", i, [i, d, d, vp, vp, vp, vp])
+    proto("stabgpu_chebyd", i, [i, vp])
+    proto("stabgpu_spline", i, [i, vp, vp, vp])
+    proto("stabgpu_speval", i, [i, vp, vp, vp, d, _dp])
+    proto("stabgpu_getmean_table", i, [i, vp, i, vp, vp])
+    proto("stabgpu_read_profile", i, [cp, _ip, vp, i])
+    proto("stabgpu_mean_gradients", i, [i, i, vp, vp, vp, vp, vp, vp, vp, vp])
+    proto("stabgpu_circh", i, [_dp, i, vp, vp])
+    proto("stabgpu_temporal_batch", i, [_pp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp])
+    proto("stabgpu_spatial_batch", i, [_pp, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp])
+    proto("stabgpu_zgeev_batch", i, [i, i, vp, i, vp, vp, vp])
+    proto("stabgpu_temporal_polish", i, [_pp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, d, vp, vp, _dp, _ip])
+    proto("stabgpu_temporal_assemble", i, [_pp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+    proto("stabgpu_spatial_assemble", i, [_pp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+    proto("stabgpu_debug_stages", i, [i, vp, vp, vp, _ip, _ip, vp, vp])
+    proto("stabgpu_plan_create", i, [C.POINTER(vp), i, _pp, vp, vp, vp, vp, vp, vp, i, i])
+    proto("stabgpu_plan_upload", i, [vp, i, vp, vp, vp, vp])
+    proto("stabgpu_plan_execute", i, [vp])
+    proto("stabgpu_plan_download", i, [vp, vp, vp, vp])
+    proto("stabgpu_plan_stage_times", i, [vp, C.POINTER(C.c_float)])
+    proto("stabgpu_plan_launch_count", C.c_longlong, [vp])
+    proto("stabgpu_plan_stream", vp, [vp])
+    proto("stabgpu_plan_capacity", i, [vp])
+    proto("stabgpu_plan_eig_dev", vp, [vp])
+    proto("stabgpu_plan_destroy", i, [vp])
+    proto("stabgpu_mtemporal_points", i, [d, d, d, d, d, d, vp, vp, i])
+    proto("stabgpu_mspatial_points", i, [d, d, d, d, d, d, vp, vp, i])
+    proto("stabgpu_shard_range", None, [i, i, i, _ip, _ip])
+    proto("stabgpu_write_eig_file", i, [cp, _pp, i, i, vp, vp, vp, d, vp, vp, vp, vp, vp, vp])
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().stabgpu_last_error()
+        raise StabGpuError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def _f64(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        assert a.shape == tuple(shape), (a.shape, shape)
+    return a
+
+
+def _c128(a) -> np.ndarray:
+    return np.ascontiguousarray(np.atleast_1d(a), dtype=np.complex128)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _colmajor(a: np.ndarray) -> np.ndarray:
+    """(rows, cols) numpy array -> flat column-major buffer."""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)
+
+
+# ---- host-side pieces -----------------------------------------------------------------------------
+def edge_properties(p: Params, T0: float = 0.0) -> Params:
+    _check(lib().stabgpu_edge_properties(C.byref(p), float(T0)), "stabgpu_edge_properties")
+    return p
+
+
+def sgengrid(ny: int, yi: float, ymax: float):
+    y, eta, deta, d2eta = (np.empty(ny) for _ in range(4))
+    _check(lib().stabgpu_sgengrid(ny, yi, ymax, _ptr(y), _ptr(eta), _ptr(deta), _ptr(d2eta)), "stabgpu_sgengrid")
+    return y, eta, deta, d2eta
+
+
+def chebyd(N: int) -> np.ndarray:
+    buf = np.empty((N + 1, N + 1))
+    _check(lib().stabgpu_chebyd(N, _ptr(buf)), "stabgpu_chebyd")
+    return buf.T.copy()      # buffer is column-major
+
+
+def read_profile(path: str, max_rows: int = 100000) -> np.ndarray:
+    tab = np.empty((max_rows, 6))
+    n = C.c_int(0)
+    _check(lib().stabgpu_read_profile(path.encode(), C.byref(n), _ptr(tab), max_rows), "stabgpu_read_profile")
+    return tab[: n.value].copy()
+
+
+def getmean(table: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """getmean.f90:27-111 -> vm (ny, 5)."""
+    table = _f64(table)
+    y = _f64(y)
+    ny = y.size
+    buf = np.empty((5, ny))
+    _check(lib().stabgpu_getmean_table(table.shape[0], _ptr(table), ny, _ptr(y), _ptr(buf)), "stabgpu_getmean_table")
+    return buf.T.copy()
+
+
+def mean_gradients(vm: np.ndarray, deta, d2eta, wallt: int = 0):
+    """temporal.f90:135-179 -> D1, D2 (ny, ny), Dt2 wall row, g2vm, g22vm (ny, 5)."""
+    ny = vm.shape[0]
+    vmc, deta, d2eta = _colmajor(vm), _f64(deta), _f64(d2eta)
+    D1, D2 = np.empty((ny, ny)), np.empty((ny, ny))
+    Dt2w, g2, g22 = np.empty(ny), np.empty((5, ny)), np.empty((5, ny))
+    _check(lib().stabgpu_mean_gradients(ny, wallt, _ptr(vmc), _ptr(deta), _ptr(d2eta), _ptr(D1), _ptr(D2), _ptr(Dt2w),
+                                        _ptr(g2), _ptr(g22)), "stabgpu_mean_gradients")
+    return D1.T.copy(), D2.T.copy(), Dt2w, g2.T.copy(), g22.T.copy()
+
+
+def circh(radius: float, y: np.ndarray):
+    """circh.f90:35-188 -> (x_out, h5 (ny, 5))."""
+    y = _f64(y)
+    x = C.c_double(radius)
+    buf = np.empty((5, y.size))
+    _check(lib().stabgpu_circh(C.byref(x), y.size, _ptr(y), _ptr(buf)), "stabgpu_circh")
+    return x.value, buf.T.copy()
+
+
+def mtemporal_points(amin, amax, ainc, bmin, bmax, binc):
+    n = lib().stabgpu_mtemporal_points(amin, amax, ainc, bmin, bmax, binc, None, None, 0)
+    a, b = np.empty(n), np.empty(n)
+    lib().stabgpu_mtemporal_points(amin, amax, ainc, bmin, bmax, binc, _ptr(a), _ptr(b), n)
+    return a, b
+
+
+def mspatial_points(omin, omax, oinc, bmin, bmax, binc):
+    n = lib().stabgpu_mspatial_points(omin, omax, oinc, bmin, bmax, binc, None, None, 0)
+    a, b = np.empty(n), np.empty(n)
+    lib().stabgpu_mspatial_points(omin, omax, oinc, bmin, bmax, binc, _ptr(a), _ptr(b), n)
+    return a, b
+
+
+def shard_range(npts: int, rank: int, world: int):
+    lo, hi = C.c_int(0), C.c_int(0)
+    lib().stabgpu_shard_range(npts, rank, world, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def write_eig_file(path: str, p: Params, itype: int, ind: int, omega: complex, alpha: complex, beta: complex, x: float,
+                   y, eta, deta, d2eta, eig: np.ndarray, evec: Optional[np.ndarray]):
+    """temporal.f90:883-890 / spatial.f90:1120-1126; evec is (n, n) with eigenvectors in columns."""
+    om, al, be = _c128(omega), _c128(alpha), _c128(beta)
+    eig = _c128(eig)
+    ev = None if evec is None else np.ascontiguousarray(np.asarray(evec, dtype=np.complex128).T)
+    _check(lib().stabgpu_write_eig_file(path.encode(), C.byref(p), itype, ind, _ptr(om), _ptr(al), _ptr(be), float(x),
+                                        _ptr(_f64(y)), _ptr(_f64(eta)), _ptr(_f64(deta)), _ptr(_f64(d2eta)), _ptr(eig),
+                                        _ptr(ev)), "stabgpu_write_eig_file")
+
+
+# ---- device ---------------------------------------------------------------------------------------
+def init(device: int = -1):
+    _check(lib().stabgpu_init(device), "stabgpu_init")
+
+
+def device_info():
+    name = C.create_string_buffer(256)
+    sm, mem = C.c_int(0), C.c_double(0.0)
+    _check(lib().stabgpu_device_info(name, 256, C.byref(sm), C.byref(mem)), "stabgpu_device_info")
+    return name.value.decode(), sm.value, mem.value
+
+
+def set_tuning(qr_window=0, qr_shifts=0, qr_threads=0, hess_threads=0):
+    _check(lib().stabgpu_set_tuning(qr_window, qr_shifts, qr_threads, hess_threads), "stabgpu_set_tuning")
+
+
+def _grid_args(p: Params, vm, g2vm, g22vm, deta, d2eta):
+    ny = p.ny
+    vmc = _colmajor(_f64(vm, (ny, 5)))
+    g2c = None if g2vm is None else _colmajor(_f64(g2vm, (ny, 5)))
+    g22c = None if g22vm is None else _colmajor(_f64(g22vm, (ny, 5)))
+    return vmc, g2c, g22c, _f64(deta, (ny,)), _f64(d2eta, (ny,))
+
+
+def _evec_out(buf: np.ndarray) -> np.ndarray:
+    """(npts, col, row) column-major buffers -> (npts, row, col) views with eigenvectors in columns."""
+    return buf.transpose(0, 2, 1)
+
+
+def temporal_batch(p: Params, vm, deta, d2eta, alpha: Sequence[complex], beta: Sequence[complex], g2vm=None, g22vm=None,
+                   Re_pt=None, Ma_pt=None, want_vectors: bool = False, out=None):
+    """stabgpu_temporal_batch -> (omg (npts, n), evec (npts, n, n) or None, info (npts,)).
+    `out` = (omg, evec_buffer, info) preallocated host buffers (e.g. pinned); the evec buffer is in
+    the library's layout (npts, column, row)."""
+    vmc, g2c, g22c, de, d2e = _grid_args(p, vm, g2vm, g22vm, deta, d2eta)
+    al, be = _c128(alpha), _c128(beta)
+    npts, n = al.size, NDOF * p.ny
+    assert be.size == npts
+    re = None if Re_pt is None else _f64(Re_pt, (npts,))
+    ma = None if Ma_pt is None else _f64(Ma_pt, (npts,))
+    if out is not None:
+        omg, ev, info = out
+    else:
+        omg = np.empty((npts, n), dtype=np.complex128)
+        ev = np.empty((npts, n, n), dtype=np.complex128) if want_vectors else None
+        info = np.zeros(npts, dtype=np.int32)
+    _check(lib().stabgpu_temporal_batch(C.byref(p), _ptr(vmc), _ptr(g2c), _ptr(g22c), _ptr(de), _ptr(d2e), npts, _ptr(al),
+                                        _ptr(be), _ptr(re), _ptr(ma), 1 if want_vectors else 0, _ptr(omg), _ptr(ev),
+                                        _ptr(info)), "stabgpu_temporal_batch")
+    return omg, (None if ev is None else _evec_out(ev)), info
+
+
+def spatial_batch(p: Params, vm, deta, d2eta, omega: Sequence[complex], beta: Sequence[complex], h5=None, g2vm=None,
+                  g22vm=None, Re_pt=None, Ma_pt=None, want_vectors: bool = False, out=None):
+    """stabgpu_spatial_batch -> (alp (npts, 2n), evec (npts, 2n, 2n) or None, info)."""
+    vmc, g2c, g22c, de, d2e = _grid_args(p, vm, g2vm, g22vm, deta, d2eta)
+    h5c = None if h5 is None else _colmajor(_f64(h5, (p.ny, 5)))
+    om, be = _c128(omega), _c128(beta)
+    npts, N = om.size, 2 * NDOF * p.ny
+    assert be.size == npts
+    re = None if Re_pt is None else _f64(Re_pt, (npts,))
+    ma = None if Ma_pt is None else _f64(Ma_pt, (npts,))
+    if out is not None:
+        alp, ev, info = out
+    else:
+        alp = np.empty((npts, N), dtype=np.complex128)
+        ev = np.empty((npts, N, N), dtype=np.complex128) if want_vectors else None
+        info = np.zeros(npts, dtype=np.int32)
+    _check(lib().stabgpu_spatial_batch(C.byref(p), _ptr(vmc), _ptr(g2c), _ptr(g22c), _ptr(de), _ptr(d2e), _ptr(h5c), npts,
+                                       _ptr(om), _ptr(be), _ptr(re), _ptr(ma), 1 if want_vectors else 0, _ptr(alp), _ptr(ev),
+                                       _ptr(info)), "stabgpu_spatial_batch")
+    return alp, (None if ev is None else _evec_out(ev)), info
+
+
+def zgeev_batch(A: np.ndarray, want_vectors: bool = False):
+    """A: (batch, n, n) complex.  Returns (w (batch, n), V (batch, n, n) or None, info)."""
+    A = np.asarray(A, dtype=np.complex128)
+    if A.ndim == 2:
+        A = A[None]
+    batch, n, _ = A.shape
+    Ac = np.ascontiguousarray(A.transpose(0, 2, 1))
+    w = np.empty((batch, n), dtype=np.complex128)
+    V = np.empty((batch, n, n), dtype=np.complex128) if want_vectors else None
+    info = np.zeros(batch, dtype=np.int32)
+    _check(lib().stabgpu_zgeev_batch(n, batch, _ptr(Ac), 1 if want_vectors else 0, _ptr(w), _ptr(V), _ptr(info)),
+           "stabgpu_zgeev_batch")
+    return w, (None if V is None else _evec_out(V)), info
+
+
+def temporal_assemble(p: Params, vm, deta, d2eta, alpha: complex, beta: complex, g2vm=None, g22vm=None):
+    vmc, g2c, g22c, de, d2e = _grid_args(p, vm, g2vm, g22vm, deta, d2eta)
+    n = NDOF * p.ny
+    A0, B0 = np.empty((n, n), dtype=np.complex128), np.empty((n, n), dtype=np.complex128)
+    al, be = _c128(alpha), _c128(beta)
+    _check(lib().stabgpu_temporal_assemble(C.byref(p), _ptr(vmc), _ptr(g2c), _ptr(g22c), _ptr(de), _ptr(d2e), _ptr(al),
+                                           _ptr(be), _ptr(A0), _ptr(B0)), "stabgpu_temporal_assemble")
+    return A0.T, B0.T
+
+
+def spatial_assemble(p: Params, vm, deta, d2eta, omega: complex, beta: complex, h5=None, g2vm=None, g22vm=None):
+    vmc, g2c, g22c, de, d2e = _grid_args(p, vm, g2vm, g22vm, deta, d2eta)
+    h5c = None if h5 is None else _colmajor(_f64(h5, (p.ny, 5)))
+    n = NDOF * p.ny
+    Cs = [np.empty((n, n), dtype=np.complex128) for _ in range(3)]
+    om, be = _c128(omega), _c128(beta)
+    _check(lib().stabgpu_spatial_assemble(C.byref(p), _ptr(vmc), _ptr(g2c), _ptr(g22c), _ptr(de), _ptr(d2e), _ptr(h5c),
+                                          _ptr(om), _ptr(be), _ptr(Cs[0]), _ptr(Cs[1]), _ptr(Cs[2])),
+           "stabgpu_spatial_assemble")
+    return tuple(c.T for c in Cs)
+
+
+def debug_stages(A: np.ndarray):
+    """Balanced matrix, scale, ilo, ihi, Hessenberg(+reflectors), tau of one matrix (stage parity tests)."""
+    A = np.asarray(A, dtype=np.complex128)
+    n = A.shape[0]
+    Ac = np.ascontiguousarray(A.T)
+    bal, hess = np.empty((n, n), dtype=np.complex128), np.empty((n, n), dtype=np.complex128)
+    scale, tau = np.empty(n), np.empty(n, dtype=np.complex128)
+    ilo, ihi = C.c_int(0), C.c_int(0)
+    _check(lib().stabgpu_debug_stages(n, _ptr(Ac), _ptr(bal), _ptr(scale), C.byref(ilo), C.byref(ihi), _ptr(hess), _ptr(tau)),
+           "stabgpu_debug_stages")
+    return bal.T, scale, ilo.value, ihi.value, hess.T, tau
+
+
+class Plan:
+    """Device-resident plan (stabgpu_plan_*): upload sweep values, execute kernels, download results."""
+
+    def __init__(self, kind: int, p: Params, vm, deta, d2eta, max_pts: int, want_vectors: bool = False, h5=None,
+                 g2vm=None, g22vm=None):
+        vmc, g2c, g22c, de, d2e = _grid_args(p, vm, g2vm, g22vm, deta, d2eta)
+        h5c = None if h5 is None else _colmajor(_f64(h5, (p.ny, 5)))
+        self._h = C.c_void_p()
+        self.kind, self.p = kind, p.copy()
+        self.N = (1 if kind == 1 else 2) * NDOF * p.ny
+        self.want_vectors = bool(want_vectors)
+        _check(lib().stabgpu_plan_create(C.byref(self._h), kind, C.byref(p), _ptr(vmc), _ptr(g2c), _ptr(g22c), _ptr(de),
+                                         _ptr(d2e), _ptr(h5c), max_pts, 1 if want_vectors else 0), "stabgpu_plan_create")
+        self.capacity = lib().stabgpu_plan_capacity(self._h)
+        self.npts = 0
+
+    def upload(self, s1, s2, Re_pt=None, Ma_pt=None):
+        s1, s2 = _c128(s1), _c128(s2)
+        self.npts = s1.size
+        re = None if Re_pt is None else _f64(Re_pt, (self.npts,))
+        ma = None if Ma_pt is None else _f64(Ma_pt, (self.npts,))
+        _check(lib().stabgpu_plan_upload(self._h, self.npts, _ptr(s1), _ptr(s2), _ptr(re), _ptr(ma)), "stabgpu_plan_upload")
+
+    def execute(self):
+        _check(lib().stabgpu_plan_execute(self._h), "stabgpu_plan_execute")
+
+    def download(self, eig: Optional[np.ndarray] = None, evec: Optional[np.ndarray] = None, info: Optional[np.ndarray] = None):
+        """Buffers may be preallocated (e.g. pinned); evec buffer layout is (npts, col, row)."""
+        if eig is None:
+            eig = np.empty((self.npts, self.N), dtype=np.complex128)
+        if evec is None and self.want_vectors:
+            evec = np.empty((self.npts, self.N, self.N), dtype=np.complex128)
+        if info is None:
+            info = np.zeros(self.npts, dtype=np.int32)
+        _check(lib().stabgpu_plan_download(self._h, _ptr(eig), _ptr(evec), _ptr(info)), "stabgpu_plan_download")
+        return eig, (None if evec is None else _evec_out(evec)), info
+
+    def stage_times(self) -> dict:
+        ms = (C.c_float * 8)()
+        lib().stabgpu_plan_stage_times(self._h, ms)
+        names = ("assemble", "lu", "balance", "hessenberg", "prep", "qr", "sort", "evec")
+        return dict(zip(names, (float(v) for v in ms)))
+
+    def launch_count(self) -> int:
+        return int(lib().stabgpu_plan_launch_count(self._h))
+
+    def stream(self) -> int:
+        return int(lib().stabgpu_plan_stream(self._h) or 0)
+
+    def eig_dev(self) -> int:
+        """Device address of the sorted eigenvalues (N x npts complex128, column-major)."""
+        return int(lib().stabgpu_plan_eig_dev(self._h) or 0)
+
+    def destroy(self):
+        if self._h:
+            lib().stabgpu_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

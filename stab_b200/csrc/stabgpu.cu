@@ -81,6 +81,7 @@ struct stabgpu_plan {
   stabgpu_params prm;
   int ny = 0, n = 0, N = 0; // n = 5 ny, N = order of the eigenproblem (n or 2n)
   int cap = 0, npts = 0;
+  bool cap_limited = false;   // cap was clipped by device memory
   int want_vectors = 0;
   cudaStream_t stream = nullptr;
   // grid / profile
@@ -127,6 +128,7 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
   if ((size_t)cap > capmem) cap = (int)capmem;
   if (cap > 65535) cap = 65535;
   if (cap < 1) return fail("libstabgpu: not enough device memory for a single point");
+  pl->cap_limited = cap < max_pts;
   pl->cap = cap;
   const int N = pl->N, n = pl->n, ny = pl->ny;
   if (pl->s1.alloc(cap) || pl->s2.alloc(cap) || pl->Re.alloc(cap) || pl->Ma.alloc(cap)) return 1;
@@ -237,6 +239,8 @@ int check_params(const stabgpu_params* p) {
 
 }  // namespace
 
+static stabgpu_plan* g_cached = nullptr;
+
 extern "C" {
 
 const char* stabgpu_last_error(void) { return g_err.c_str(); }
@@ -248,6 +252,7 @@ int stabgpu_init(int device) {
 }
 
 int stabgpu_finalize(void) {
+  if (g_cached) { stabgpu_plan_destroy(g_cached); g_cached = nullptr; }
   if (g_inited) cudaDeviceSynchronize();
   g_inited = false;
   return 0;
@@ -366,13 +371,22 @@ int stabgpu_plan_stage_times(stabgpu_plan* pl, float* ms) {
 
 long long stabgpu_plan_launch_count(stabgpu_plan* pl) { return pl ? pl->launches : 0; }
 
+void* stabgpu_plan_stream(stabgpu_plan* pl) { return pl ? (void*)pl->stream : nullptr; }
+int stabgpu_plan_capacity(stabgpu_plan* pl) { return pl ? pl->cap : 0; }
+
+void* stabgpu_plan_eig_dev(stabgpu_plan* pl) { return pl ? (void*)pl->eig.p : nullptr; }
+
 int stabgpu_plan_destroy(stabgpu_plan* pl) {
   if (!pl) return 0;
+  if (pl == g_cached) g_cached = nullptr;
   if (pl->stream) cudaStreamDestroy(pl->stream);
   for (int i = 0; i <= ST_N; ++i) if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
   delete pl;
   return 0;
 }
+
+// The batch entry points keep ONE plan (device workspace) alive between calls: a sweep driver calls
+// them repeatedly with the same problem shape, and cudaMalloc of GBs per call would dominate.
 
 static int batch_common(int kind, const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
                         const double* deta, const double* d2eta, const double* h5, int npts, const double* s1,
@@ -380,8 +394,20 @@ static int batch_common(int kind, const stabgpu_params* p, const double* vm, con
                         double* evec, int* info) {
   if (npts < 1 || !s1 || !s2 || !eig) return fail("libstabgpu: bad argument");
   if (want_vectors && !evec) return fail("libstabgpu: want_vectors set but evec is NULL");
-  stabgpu_plan* pl = nullptr;
-  if (stabgpu_plan_create(&pl, kind, p, vm, g2vm, g22vm, deta, d2eta, h5, npts, want_vectors)) return 1;
+  if (ensure_init()) return 1;
+  if (check_params(p)) return 1;
+  stabgpu_plan* pl = g_cached;
+  if (pl && (pl->kind != kind || pl->ny != p->ny || pl->want_vectors != (want_vectors ? 1 : 0) || (pl->cap < npts && !pl->cap_limited))) {
+    stabgpu_plan_destroy(pl);
+    pl = g_cached = nullptr;
+  }
+  if (!pl) {
+    if (stabgpu_plan_create(&pl, kind, p, vm, g2vm, g22vm, deta, d2eta, h5, npts, want_vectors)) return 1;
+    g_cached = pl;
+  } else {
+    pl->prm = *p;
+    if (upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, h5)) return 1;
+  }
   const int N = pl->N;
   int rc = 0;
   for (int p0 = 0; p0 < npts && !rc; p0 += pl->cap) {
@@ -391,7 +417,6 @@ static int batch_common(int kind, const stabgpu_params* p, const double* vm, con
     if (!rc) rc = stabgpu_plan_download(pl, eig + 2 * (size_t)p0 * N, want_vectors ? evec + 2 * (size_t)p0 * N * N : nullptr,
                                         info ? info + p0 : nullptr);
   }
-  stabgpu_plan_destroy(pl);
   return rc;
 }
 

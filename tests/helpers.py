@@ -1,0 +1,92 @@
+"""Shared test helpers: oracle <-> product parameter conversion, spectrum matching, emulation build."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import stab_oracle as so
+from conftest import GOLDEN, ROOT, golden_text
+
+import stab_b200 as sb
+
+
+def to_params(p: "so.Params") -> "sb.Params":
+    q = sb.Params.default()
+    q.ny, q.mattyp, q.wallt, q.top, q.curve = p.ny, p.mattyp, p.wallt, p.top, p.curve
+    q.ider, q.ievec, q.wall = p.ider, p.ievec, p.wall
+    q.Ma, q.Re, q.Pr = p.Ma, p.Re, p.Pr
+    q.gamma, q.gamma1, q.cp = p.gamma, p.gamma1, p.cp
+    q.Te, q.rmue, q.rlme, q.cone = p.Te, p.rmue, p.rlme, p.cone
+    for k in range(3):
+        q.datmat[k] = p.datmat[k]
+    q.yi, q.ymax, q.x = p.yi, p.ymax, p.x
+    return q
+
+
+def oracle_case(deck, prof, **over):
+    """deck + profile -> (oracle params, grid dict incl. hm/h5 for spatial)."""
+    p = so.read_deck(golden_text(deck))
+    for k, v in over.items():
+        setattr(p, k, v)
+    p.finish()
+    g = so.prepare(p, golden_text(prof))
+    if p.itype == 2:
+        x_out, hm = so.curvature_metrics(p, g["y"])
+        g["hm"] = hm
+        g["h5"] = np.stack(hm, axis=1)
+        g["x_out"] = x_out
+    return p, g
+
+
+def match_spectra(a: np.ndarray, b: np.ndarray):
+    """Greedy nearest-neighbour matching of two spectra as multisets.  Returns (perm, dist) with
+    b[perm[k]] matched to a[k]."""
+    a = np.asarray(a); b = np.asarray(b)
+    from scipy.optimize import linear_sum_assignment
+    n = a.size
+    if n <= 400:
+        cost = np.abs(a[:, None] - b[None, :])
+        r, c = linear_sum_assignment(cost)
+        return c, cost[r, c]
+    # large: sort-based candidate then local assignment is overkill; nearest neighbour with removal
+    perm = np.empty(n, dtype=int)
+    used = np.zeros(n, dtype=bool)
+    order = np.argsort(-np.abs(a))
+    for k in order:
+        d = np.abs(b - a[k])
+        d[used] = np.inf
+        j = int(np.argmin(d))
+        perm[k] = j
+        used[j] = True
+    return perm, np.abs(a - b[perm])
+
+
+def eigpair_residuals(M: np.ndarray, w: np.ndarray, V: np.ndarray) -> np.ndarray:
+    """|| M v - w v ||_2 / (||M||_F ||v||_2) per column."""
+    R = M @ V - V * w[None, :]
+    return np.linalg.norm(R, axis=0) / (np.linalg.norm(M) * np.linalg.norm(V, axis=0))
+
+
+# ---- emulation library (single-threaded host trace of the kernel source) ------------------------
+_emu = None
+
+
+def emu():
+    global _emu
+    if _emu is not None:
+        return _emu
+    src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
+    hm = os.path.join(ROOT, "stab_b200", "csrc", "host_math.cpp")
+    out = os.path.join(ROOT, "tests", "emu", "libstabemu.so")
+    deps = [src, hm] + [os.path.join(ROOT, "stab_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "stab_b200", "csrc"))
+                        if f.endswith(".cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DSTAB_EMU", "-ffp-contract=off",
+                               "-o", out, src, hm])
+    _emu = C.CDLL(out)
+    return _emu
+
+
+def cptr(a):
+    return a.ctypes.data_as(C.c_void_p)
