@@ -29,7 +29,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--points", type=int, default=256, help="sweep points per GPU per step (weak scaling)")
+    ap.add_argument("--points", type=int, default=296, help="sweep points per GPU per step (weak scaling)")
     ap.add_argument("--ny", type=int, default=128)
     ap.add_argument("--no-vectors", action="store_true", help="eigenvalues only (the reference always computes vectors)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])

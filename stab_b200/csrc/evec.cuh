@@ -94,7 +94,8 @@ SD_DEV void warp_apply_q(const Cta& w, const cplx* A, int lda, int ilo, int ihi,
 
 // ZGEBAK('B','R'): undo scaling on [ilo,ihi], then the permutations
 SD_DEV void warp_gebak(const Cta& w, int n, int ilo, int ihi, const double* scale, cplx* x) {
-  for (int r = ilo + w.lane; r <= ihi; r += w.ws) x[r] = x[r] * scale[r];
+  if (ilo != ihi)                             // ZGEBAK skips the scaling when ILO == IHI (scale(ilo) may hold a permutation)
+    for (int r = ilo + w.lane; r <= ihi; r += w.ws) x[r] = x[r] * scale[r];
   warp_sync();
   if (w.lane == 0) {
     for (int i = ilo - 1; i >= 0; --i) {
@@ -172,9 +173,14 @@ SD_DEV void warp_scale_maxabs(const Cta& w, int nrows, cplx* x) {
 // Full per-eigenvalue pipeline executed by one warp.  Returns 0 or 1 (no growth / non-finite).
 //   Hh  : Hessenberg matrix with the reflectors still stored below the subdiagonal (ZGEHRD layout);
 //         entries below the first subdiagonal are ignored by construction of the solver.
+//   kr  : last index of the diagonal block of H (between exactly-zero subdiagonals) the eigenvalue
+//         belongs to.  As ZHSEIN does, the vector is computed from the leading (kr+1) x (kr+1)
+//         submatrix and is exactly zero below: a solve with the whole matrix would pick up
+//         cond(H22 - lam I) * eps garbage in the decoupled trailing part.
 SD_DEV int warp_eigvec(const Cta& w, const cplx* Hh, int n, int ldh, int ilo, int ihi, const cplx* tau,
-                       const double* scale, cplx lam, double hnorm, int scale_rows, cplx* c, cplx* y,
+                       const double* scale, cplx lam, int kr, double hnorm, int scale_rows, cplx* c, cplx* y,
                        unsigned char* flag, cplx* out) {
+  const int m = kr + 1;
   const double smlnum = SD_SAFMIN * ((double)n / SD_ULP);
   const double eps3 = fmax(SD_ULP * hnorm, smlnum);
   const double rootn = sqrt((double)n);
@@ -182,18 +188,20 @@ SD_DEV int warp_eigvec(const Cta& w, const cplx* Hh, int n, int ldh, int ilo, in
   const double bscale = eps3;                 // |b_i| ~ eps3 as in ZLAEIN
   int bad = 1;
   for (int its = 0; its < 4; ++its) {
-    warp_hess_solve(w, Hh, n, ldh, lam, eps3, bscale, its, c, y, flag);
+    warp_hess_solve(w, Hh, m, ldh, lam, eps3, bscale, its, c, y, flag);
     double vn = 0.0;
-    for (int r = w.lane; r < n; r += w.ws) vn += cabs1(y[r]);
+    for (int r = w.lane; r < m; r += w.ws) vn += cabs1(y[r]);
     vn = warp_sum(vn);
     if (!(vn == vn) || vn > 1.0e300) break;   // NaN / overflow
     if (vn >= growto) { bad = 0; break; }                 // ZLAEIN's growth test
   }
   if (bad) {
     // no acceptable vector: return the unit vector of the last attempt's largest entry
-    for (int r = w.lane; r < n; r += w.ws) y[r] = mk(r == 0 ? 1.0 : 0.0, 0.0);
+    for (int r = w.lane; r < m; r += w.ws) y[r] = mk(r == 0 ? 1.0 : 0.0, 0.0);
     warp_sync();
   }
+  for (int r = m + w.lane; r < n; r += w.ws) y[r] = mk(0.0, 0.0);
+  warp_sync();
   warp_apply_q(w, Hh, ldh, ilo, ihi, tau, y);
   warp_gebak(w, n, ilo, ihi, scale, y);
   warp_normalize_zgeev(w, n, y);

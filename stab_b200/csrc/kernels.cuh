@@ -197,7 +197,7 @@ __global__ void k_hessenberg(cplx* A, size_t astride, int n, const int* ilohi, c
 
 // ---- stage 3c: prepare the QR operand: Hq := upper Hessenberg part of A (zeros below), plus the
 // infinity norm of H for the inverse-iteration tolerances.  Hq may alias A (eigenvalues-only path).
-__global__ void k_prep_qr(const cplx* A, size_t astride, cplx* Hq, size_t hstride, int n, double* hnorm) {
+__global__ void k_prep_qr(const cplx* A, size_t astride, cplx* Hq, size_t hstride, int n, double* hnorm, int* blkend) {
   __shared__ double red[160];
   Cta c = make_cta(red);
   const int p = blockIdx.x;
@@ -211,7 +211,16 @@ __global__ void k_prep_qr(const cplx* A, size_t astride, cplx* Hq, size_t hstrid
   }
   double dummy = 0.0;
   cta_max2(c, mx, dummy);
-  if (c.tid == 0) hnorm[p] = mx;
+  if (c.tid == 0) {
+    hnorm[p] = mx;
+    // diagonal blocks of H separated by exactly-zero subdiagonals (ZHSEIN's KL..KR with FROMQR):
+    // blkend[i] = last index of the block containing i
+    int end = n - 1;
+    for (int i = n - 1; i >= 0; --i) {
+      if (i < n - 1 && is_zero(a[(i + 1) + (size_t)i * n])) end = i;
+      blkend[(size_t)p * n + i] = end;
+    }
+  }
   for (int j = 0; j < n; ++j)
     for (int r = c.tid; r < n; r += c.nt) {
       cplx v = a[r + (size_t)j * n];
@@ -257,11 +266,12 @@ __global__ void k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w
 // (spatial.f90:1065-1084).  mode 0: no sort (generic solver).
 // out: sorted eigenvalue (omega or alpha); lam: the matrix eigenvalue in the same order, perturbed
 // like ZHSEIN does for (nearly) coincident values so inverse iteration yields independent vectors.
-__global__ void k_sort(const cplx* w, int n, int mode, const double* hnorm, cplx* out, cplx* lam) {
+__global__ void k_sort(const cplx* w, int n, int mode, const double* hnorm, const int* blkend, cplx* out, cplx* lam, int* kr) {
   const int p = blockIdx.x;
   const cplx* wp = w + (size_t)p * n;
   cplx* op = out + (size_t)p * n;
   cplx* lp = lam + (size_t)p * n;
+  const int* be = blkend + (size_t)p * n;
   const double eps3 = fmax(SD_ULP * hnorm[p], SD_SAFMIN * ((double)n / SD_ULP));
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     cplx wi = wp[i];
@@ -278,17 +288,18 @@ __global__ void k_sort(const cplx* w, int n, int mode, const double* hnorm, cplx
         if (kj < key || (kj == key && j < i)) ++rank;
       }
     }
-    int close = 0;   // earlier (in input order) eigenvalues closer than eps3
-    for (int j = 0; j < i; ++j) if (cabs1(wp[j] - wi) < eps3) ++close;
+    int close = 0;   // earlier eigenvalues of the same diagonal block closer than eps3 (ZHSEIN)
+    for (int j = 0; j < i; ++j) if (be[j] == be[i] && cabs1(wp[j] - wi) < eps3) ++close;
     op[rank] = vi;
     lp[rank] = wi + mk(eps3 * close, 0.0);
+    kr[(size_t)p * n + rank] = be[i];
   }
 }
 
 // ---- stage 6: eigenvectors ----------------------------------------------------------------------
 // grid (chunks, batch); each warp takes eigen-indices e = chunk*warps + wid, += chunks*warps
 __global__ void k_evec(const cplx* Hh, size_t hstride, int n, const int* ilohi, const cplx* tau, const double* scale,
-                       const cplx* lam, const double* hnorm, int scale_rows, cplx* V, size_t vstride, int* vinfo) {
+                       const cplx* lam, const int* kr, const double* hnorm, int scale_rows, cplx* V, size_t vstride, int* vinfo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta w = make_cta(nullptr);
   const int p = blockIdx.y;
@@ -299,7 +310,8 @@ __global__ void k_evec(const cplx* Hh, size_t hstride, int n, const int* ilohi, 
   int bad = 0;
   for (int e = blockIdx.x * w.nw + w.wid; e < n; e += gridDim.x * w.nw) {
     bad += warp_eigvec(w, Hh + (size_t)p * hstride, n, n, ilo, ihi, tau + (size_t)p * n, scale + (size_t)p * n,
-                       lam[(size_t)p * n + e], hnorm[p], scale_rows, cvec, yvec, flag, V + (size_t)p * vstride + (size_t)e * n);
+                       lam[(size_t)p * n + e], kr[(size_t)p * n + e], hnorm[p], scale_rows, cvec, yvec, flag,
+                       V + (size_t)p * vstride + (size_t)e * n);
   }
   if (bad && w.lane == 0) atomicAdd(vinfo + p, bad);
 }

@@ -94,7 +94,7 @@ struct stabgpu_plan {
   // work
   DBuf<cplx> coef, A, C, Hq, V, tau, w, eig, lam;
   DBuf<double> scale, hnorm;
-  DBuf<int> cnt, ilohi, info_lu, info_qr, info_v;
+  DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr;
   cudaEvent_t ev[ST_N + 1] = {};
   float ms[ST_N] = {};
   long long launches = 0;
@@ -115,7 +115,7 @@ size_t per_point_bytes(int kind, int n, int N, int ny, int want_vectors) {
   if (kind == 2) b += (size_t)n * n * 16;            // C0
   if (want_vectors) b += 2 * (size_t)N * N * 16;     // Hq + V
   b += (size_t)ny * 150 * 16;                        // coefficients
-  b += (size_t)N * (16 * 4 + 8 + 4) + 64;
+  b += (size_t)N * (16 * 4 + 8 + 4 * 3) + 64;
   return b;
 }
 
@@ -138,6 +138,7 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
   if (pl->want_vectors && (pl->Hq.alloc((size_t)cap * N * N) || pl->V.alloc((size_t)cap * N * N))) return 1;
   if (pl->tau.alloc((size_t)cap * N) || pl->w.alloc((size_t)cap * N) || pl->eig.alloc((size_t)cap * N) || pl->lam.alloc((size_t)cap * N)) return 1;
   if (pl->scale.alloc((size_t)cap * N) || pl->hnorm.alloc(cap) || pl->cnt.alloc((size_t)cap * N)) return 1;
+  if (pl->blkend.alloc((size_t)cap * N) || pl->kr.alloc((size_t)cap * N)) return 1;
   if (pl->ilohi.alloc(2 * (size_t)cap) || pl->info_lu.alloc(cap) || pl->info_qr.alloc(cap) || pl->info_v.alloc(cap)) return 1;
   CU(cudaStreamCreate(&pl->stream));
   for (int i = 0; i <= ST_N; ++i) CU(cudaEventCreate(&pl->ev[i]));
@@ -160,7 +161,7 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   }
   CU(cudaEventRecord(pl->ev[ST_HESS + 1], s));
   cplx* Hq = pl->want_vectors ? pl->Hq.p : pl->A.p;
-  k_prep_qr<<<np, 256, 0, s>>>(pl->A.p, st, Hq, st, N, pl->hnorm.p);
+  k_prep_qr<<<np, 256, 0, s>>>(pl->A.p, st, Hq, st, N, pl->hnorm.p, pl->blkend.p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(pl->ev[ST_PREP + 1], s));
   {
@@ -173,7 +174,7 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(pl->ev[ST_QR + 1], s));
-  k_sort<<<np, 256, 0, s>>>(pl->w.p, N, sort_mode, pl->hnorm.p, pl->eig.p, pl->lam.p);
+  k_sort<<<np, 256, 0, s>>>(pl->w.p, N, sort_mode, pl->hnorm.p, pl->blkend.p, pl->eig.p, pl->lam.p, pl->kr.p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(pl->ev[ST_SORT + 1], s));
   pl->launches += 5;
@@ -189,7 +190,7 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
     while (chunks * np < 2 * 148 && chunks * warps < N) chunks *= 2;
     dim3 grid(chunks, np);
     // the reflectors live in A (ZGEHRD layout); the QR ran on the copy Hq
-    k_evec<<<grid, warps * 32, sm, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->scale.p, pl->lam.p, pl->hnorm.p,
+    k_evec<<<grid, warps * 32, sm, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->scale.p, pl->lam.p, pl->kr.p, pl->hnorm.p,
                                         scale_rows, pl->V.p, st, pl->info_v.p);
     CU(cudaGetLastError());
     pl->launches += 1;

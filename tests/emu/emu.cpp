@@ -151,14 +151,23 @@ int emu_spatial_matrices(const stabgpu_params* p, const double* vm, const double
 }
 
 // Eigenvectors of the ORIGINAL matrix from (Hessenberg+reflectors, tau, scale, ilo, ihi) and eigenvalues lam
+// lam[e] must be the eigenvalue found at index position e of the Hessenberg matrix (ZHSEQR order)
 int emu_evec(const cplx* Hh, int n, int ilo, int ihi, const cplx* tau, const double* scale, const cplx* lam, int nlam,
              double hnorm, int scale_rows, cplx* V) {
+  std::vector<int> blkend(n);
+  {
+    int end = n - 1;
+    for (int i = n - 1; i >= 0; --i) {
+      if (i < n - 1 && is_zero(Hh[(i + 1) + (size_t)i * n])) end = i;
+      blkend[i] = end;
+    }
+  }
   Cta w = make_cta(nullptr);
   std::vector<cplx> c(n), y(n);
   std::vector<unsigned char> flag(n);
   int bad = 0;
   for (int e = 0; e < nlam; ++e)
-    bad += warp_eigvec(w, Hh, n, n, ilo, ihi, tau, scale, lam[e], hnorm, scale_rows, c.data(), y.data(), flag.data(), V + (size_t)e * n);
+    bad += warp_eigvec(w, Hh, n, n, ilo, ihi, tau, scale, lam[e], blkend[e], hnorm, scale_rows, c.data(), y.data(), flag.data(), V + (size_t)e * n);
   return bad;
 }
 

@@ -196,3 +196,21 @@ def test_full_pipeline_random_vectors():
     Vm = V[:, perm]
     dots = np.abs(np.sum(vr.conj() * Vm, axis=0))
     assert np.abs(dots - 1).max() < 1e-9
+
+
+def test_full_pipeline_structured_matrices():
+    """Balancing isolates eigenvalues (permutations), decoupled blocks: vectors from the leading
+    block only (ZHSEIN's KR), ZGEBAK with ILO == IHI."""
+    n = 40
+    r = np.random.default_rng(7)
+    T = np.triu(r.standard_normal((n, n)) + 1j * r.standard_normal((n, n)))
+    P = np.eye(n)[r.permutation(n)]
+    A1 = P @ T @ P.T
+    A2 = r.standard_normal((n, n)) + 0j
+    A2[5, :] = 0; A2[:, 9] = 0; A2[17, :] = 0
+    for A in (A1, A2):
+        w, V, info = emu_eig_pipeline(A)
+        assert info == 0
+        assert eigpair_residuals(A, w, V).max() < 1e-12
+        _, d = match_spectra(np.linalg.eigvals(A), w)
+        assert d.max() < 1e-9
