@@ -50,6 +50,9 @@ const char* stabgpu_last_error(void);
 int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb);
 /* tuning knobs of the QR stage (window size, shifts per sweep, threads); 0 keeps the default */
 int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads);
+/* Hessenberg stage variant: 1 (default) batched blocked reduction with DMMA tensor-core updates; 2 the same with a
+ * scalar-FMA GEMM (validation of the tensor-core path); 0 the unblocked one-CTA-per-matrix kernel of v1 */
+int stabgpu_set_hess_mode(int mode);
 
 /* ---- host-side pieces of the path (pure C++, no device) ------------------------------------------ */
 void stabgpu_params_default(stabgpu_params* p);                       /* stuff.f90 initial values */

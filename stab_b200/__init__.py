@@ -24,6 +24,7 @@ from .binding import (  # noqa: F401
     mtemporal_points,
     read_profile,
     set_tuning,
+    set_hess_mode,
     sgengrid,
     shard_range,
     spatial_assemble,

@@ -73,6 +73,7 @@ def lib():
     proto("stabgpu_last_error", cp, [])
     proto("stabgpu_device_info", i, [cp, i, _ip, _dp])
     proto("stabgpu_set_tuning", i, [i, i, i, i])
+    proto("stabgpu_set_hess_mode", i, [i])
     proto("stabgpu_params_default", None, [_pp])
     proto("stabgpu_edge_properties", i, [_pp, d])
     proto("stabgpu_sgengrid", i, [i, d, d, vp, vp, vp, vp])
@@ -234,6 +235,10 @@ def device_info():
 
 def set_tuning(qr_window=0, qr_shifts=0, qr_threads=0, hess_threads=0):
     _check(lib().stabgpu_set_tuning(qr_window, qr_shifts, qr_threads, hess_threads), "stabgpu_set_tuning")
+
+
+def set_hess_mode(mode: int):
+    lib().stabgpu_set_hess_mode(int(mode))
 
 
 def _grid_args(p: Params, vm, g2vm, g22vm, deta, d2eta):

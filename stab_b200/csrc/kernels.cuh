@@ -9,6 +9,7 @@
 #include "hqr.cuh"
 #include "evec.cuh"
 #include "lu.cuh"
+#include "hess_blocked.cuh"
 
 namespace stab {
 
@@ -193,6 +194,44 @@ __global__ void k_hessenberg(cplx* A, size_t astride, int n, const int* ilohi, c
   Cta c = make_cta(red);
   const int p = blockIdx.x;
   cta_hessenberg(c, A + (size_t)p * astride, n, n, ilohi[2 * p], ilohi[2 * p + 1], tau + (size_t)p * n, sv, sy);
+}
+
+// ---- stage 3b': batched blocked Hessenberg (hess_blocked.cuh) -------------------------------------
+__global__ void __launch_bounds__(256) k_hb_panel_step(HessBatch hb, int panel, int j) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* red = reinterpret_cast<double*>(smem_raw);
+  cplx* sb = reinterpret_cast<cplx*>(smem_raw + 160 * sizeof(double));
+  cplx* sw = sb + hb.n;
+  cplx* st = sw + HB_NB;
+  Cta c = make_cta(red);
+  cta_hb_panel_step(c, hb, blockIdx.x, panel, j, red, sb, sw, st);
+}
+
+__global__ void __launch_bounds__(HB_GEMV_ROWS) k_hb_gemv(HessBatch hb, int panel, int j) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta c = make_cta(nullptr);
+  cta_hb_gemv(c, hb, blockIdx.z, panel, j, blockIdx.x, blockIdx.y, reinterpret_cast<cplx*>(smem_raw));
+}
+
+template <int PHASE, bool USE_MMA>
+__global__ void __launch_bounds__(GEMM_THREADS) k_hb_gemm(HessBatch hb, int panel) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta c = make_cta(nullptr);
+  cta_hb_gemm<PHASE, USE_MMA>(c, hb, blockIdx.z, panel, blockIdx.x, blockIdx.y, reinterpret_cast<double*>(smem_raw));
+}
+
+__global__ void k_hb_ytop_T(HessBatch hb, int panel) {
+  Cta c = make_cta(nullptr);
+  cta_hb_ytop_T(c, hb, blockIdx.y, panel, blockIdx.x);
+}
+
+__global__ void k_hb_w_T(HessBatch hb, int panel) {
+  Cta c = make_cta(nullptr);
+  const int mat = blockIdx.y, n = hb.n;
+  const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
+  const int k = ilo + panel * HB_NB;
+  if (k >= ihi) return;
+  cta_hb_w_T(c, hb.T + ((size_t)mat * hb.P + panel) * HB_NB * HB_NB, hb.W + (size_t)mat * n * HB_NB, n - (k + HB_NB), blockIdx.x, true);
 }
 
 // ---- stage 3c: prepare the QR operand: Hq := upper Hessenberg part of A (zeros below), plus the

@@ -16,7 +16,7 @@ namespace {
 thread_local std::string g_err;
 int g_device = -1;
 bool g_inited = false;
-struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; } g_tune;
+struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
 
@@ -93,6 +93,8 @@ struct stabgpu_plan {
   bool has_Re = false, has_Ma = false;
   // work
   DBuf<cplx> coef, A, C, Hq, V, tau, w, eig, lam;
+  DBuf<cplx> hbY, hbT, hbYp, hbW;      // blocked Hessenberg workspaces
+  int hbP = 0;
   DBuf<double> scale, hnorm;
   DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr;
   cudaEvent_t ev[ST_N + 1] = {};
@@ -116,6 +118,7 @@ size_t per_point_bytes(int kind, int n, int N, int ny, int want_vectors) {
   if (want_vectors) b += 2 * (size_t)N * N * 16;     // Hq + V
   b += (size_t)ny * 150 * 16;                        // coefficients
   b += (size_t)N * (16 * 4 + 8 + 4 * 3) + 64;
+  b += (size_t)N * 16 * (3 * HB_NB + HB_CHUNKS) + 16 * HB_NB * HB_NB;   // blocked Hessenberg: Y, W, T, Ypart
   return b;
 }
 
@@ -139,9 +142,79 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
   if (pl->tau.alloc((size_t)cap * N) || pl->w.alloc((size_t)cap * N) || pl->eig.alloc((size_t)cap * N) || pl->lam.alloc((size_t)cap * N)) return 1;
   if (pl->scale.alloc((size_t)cap * N) || pl->hnorm.alloc(cap) || pl->cnt.alloc((size_t)cap * N)) return 1;
   if (pl->blkend.alloc((size_t)cap * N) || pl->kr.alloc((size_t)cap * N)) return 1;
+  pl->hbP = (N - 1 + HB_NB - 1) / HB_NB;
+  if (pl->hbY.alloc((size_t)cap * N * HB_NB) || pl->hbT.alloc((size_t)cap * pl->hbP * HB_NB * HB_NB) ||
+      pl->hbYp.alloc((size_t)cap * N * HB_CHUNKS) || pl->hbW.alloc((size_t)cap * N * HB_NB)) return 1;
   if (pl->ilohi.alloc(2 * (size_t)cap) || pl->info_lu.alloc(cap) || pl->info_qr.alloc(cap) || pl->info_v.alloc(cap)) return 1;
   CU(cudaStreamCreate(&pl->stream));
   for (int i = 0; i <= ST_N; ++i) CU(cudaEventCreate(&pl->ev[i]));
+  return 0;
+}
+
+template <int PHASE>
+int launch_hb_gemm(stabgpu_plan* pl, const HessBatch& hb, int panel, int ti, int tj, size_t smem, bool mma) {
+  dim3 grid(ti, tj, pl->npts);
+  if (mma) {
+    CU(cudaFuncSetAttribute(k_hb_gemm<PHASE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_hb_gemm<PHASE, true><<<grid, GEMM_THREADS, smem, pl->stream>>>(hb, panel);
+  } else {
+    CU(cudaFuncSetAttribute(k_hb_gemm<PHASE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_hb_gemm<PHASE, false><<<grid, GEMM_THREADS, smem, pl->stream>>>(hb, panel);
+  }
+  CU(cudaGetLastError());
+  pl->launches += 1;
+  return 0;
+}
+
+// Stage 3b: A <- Hessenberg form + reflectors (ZGEHRD layout), tau, and the panel factors T.
+int run_hessenberg(stabgpu_plan* pl) {
+  const int N = pl->N, np = pl->npts;
+  const size_t st = (size_t)N * N;
+  cudaStream_t s = pl->stream;
+  if (g_tune.hess_mode == 0) {
+    size_t sm = 160 * sizeof(double) + 2 * (size_t)N * sizeof(cplx);
+    CU(cudaFuncSetAttribute(k_hessenberg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_hessenberg<<<np, g_tune.hess_threads, sm, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p);
+    CU(cudaGetLastError());
+    pl->launches += 1;
+    return 0;
+  }
+  const bool mma = g_tune.hess_mode == 1;
+  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP};
+  const size_t sm_step = 160 * sizeof(double) + ((size_t)N + 2 * HB_NB) * sizeof(cplx);
+  const size_t sm_gemv = (size_t)N * sizeof(cplx);
+  const size_t sm64 = GemmCfg<64, 64>::smem_bytes, sm6432 = GemmCfg<64, 32>::smem_bytes, sm3264 = GemmCfg<32, 64>::smem_bytes;
+  for (int p = 0; p < pl->hbP; ++p) {
+    const int k0 = p * HB_NB;                                  // smallest possible panel start (ilo = 0)
+    const int rows_max = N - 1 - k0;                           // rows k+1..ihi
+    if (rows_max <= 0) break;
+    const int trail_max = N - (k0 + HB_NB);                    // columns k+NB..n-1
+    dim3 ggemv((rows_max + HB_GEMV_ROWS - 1) / HB_GEMV_ROWS, HB_CHUNKS, np);
+    for (int j = 0; j < HB_NB; ++j) {
+      k_hb_panel_step<<<np, 256, sm_step, s>>>(hb, p, j);
+      k_hb_gemv<<<ggemv, HB_GEMV_ROWS, sm_gemv, s>>>(hb, p, j);
+    }
+    k_hb_panel_step<<<np, 256, sm_step, s>>>(hb, p, HB_NB);
+    CU(cudaGetLastError());
+    pl->launches += 2 * HB_NB + 1;
+    const int tm = (N + 63) / 64;
+    if (launch_hb_gemm<HB_YTOP>(pl, hb, p, tm, 1, sm6432, mma)) return 1;
+    k_hb_ytop_T<<<dim3((N + 127) / 128, np), 128, 0, s>>>(hb, p);
+    pl->launches += 1;
+    if (trail_max > 0) {
+      const int tn = (trail_max + 63) / 64;
+      if (launch_hb_gemm<HB_RIGHT_TRAIL>(pl, hb, p, tm, tn, sm64, mma)) return 1;
+    }
+    if (launch_hb_gemm<HB_RIGHT_PANEL>(pl, hb, p, tm, 1, sm6432, mma)) return 1;
+    if (trail_max > 0) {
+      const int tn = (trail_max + 63) / 64;
+      if (launch_hb_gemm<HB_LEFT_W>(pl, hb, p, 1, tn, sm3264, mma)) return 1;
+      k_hb_w_T<<<dim3((trail_max + 127) / 128, np), 128, 0, s>>>(hb, p);
+      pl->launches += 1;
+      if (launch_hb_gemm<HB_LEFT_UPD>(pl, hb, p, (rows_max + 63) / 64, tn, sm64, mma)) return 1;
+    }
+    CU(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -153,12 +226,7 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   k_balance<<<np, 256, 0, s>>>(pl->A.p, st, N, pl->scale.p, pl->cnt.p, pl->ilohi.p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(pl->ev[ST_BAL + 1], s));
-  {
-    size_t sm = 160 * sizeof(double) + 2 * (size_t)N * sizeof(cplx);
-    CU(cudaFuncSetAttribute(k_hessenberg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_hessenberg<<<np, g_tune.hess_threads, sm, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p);
-    CU(cudaGetLastError());
-  }
+  if (run_hessenberg(pl)) return 1;
   CU(cudaEventRecord(pl->ev[ST_HESS + 1], s));
   cplx* Hq = pl->want_vectors ? pl->Hq.p : pl->A.p;
   k_prep_qr<<<np, 256, 0, s>>>(pl->A.p, st, Hq, st, N, pl->hnorm.p, pl->blkend.p);
@@ -177,7 +245,7 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   k_sort<<<np, 256, 0, s>>>(pl->w.p, N, sort_mode, pl->hnorm.p, pl->blkend.p, pl->eig.p, pl->lam.p, pl->kr.p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(pl->ev[ST_SORT + 1], s));
-  pl->launches += 5;
+  pl->launches += 4;
   if (pl->want_vectors) {
     CU(cudaMemsetAsync(pl->info_v.p, 0, sizeof(int) * np, s));
     int warps = 8;
@@ -268,6 +336,8 @@ int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb)
   if (mem_gb) *mem_gb = (double)pr.totalGlobalMem / 1.0e9;
   return 0;
 }
+
+int stabgpu_set_hess_mode(int mode) { g_tune.hess_mode = mode; return 0; }
 
 int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads) {
   if (qr_window > 0) g_tune.W = qr_window;
@@ -483,9 +553,8 @@ int stabgpu_debug_stages(int n, const double* A, double* balanced, double* scale
   if (ihi) *ihi = lh[1];
   if (balanced) cudaMemcpy(balanced, pl->A.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
   if (scale) cudaMemcpy(scale, pl->scale.p, sizeof(double) * n, cudaMemcpyDeviceToHost);
-  size_t sm = 160 * sizeof(double) + 2 * (size_t)n * sizeof(cplx);
-  cudaFuncSetAttribute(k_hessenberg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_hessenberg<<<1, g_tune.hess_threads, sm, s>>>(pl->A.p, st, n, pl->ilohi.p, pl->tau.p);
+  pl->npts = 1;
+  if (run_hessenberg(pl)) { stabgpu_plan_destroy(pl); return 1; }
   cudaStreamSynchronize(s);
   if (hess) cudaMemcpy(hess, pl->A.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
   if (tau) cudaMemcpy(tau, pl->tau.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost);

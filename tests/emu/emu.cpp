@@ -172,3 +172,43 @@ int emu_evec(const cplx* Hh, int n, int ilo, int ihi, const cplx* tau, const dou
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// blocked Hessenberg reduction: the batched kernel schedule of stabgpu.cu traced for one matrix
+// ---------------------------------------------------------------------------------------------
+#include "../../stab_b200/csrc/hess_blocked.cuh"
+
+extern "C" int emu_hess_blocked(cplx* A, int n, int ilo, int ihi, cplx* tau, cplx* Tout /* P*NB*NB or null */) {
+  std::vector<double> red(256);
+  Cta c = make_cta(red.data());
+  const int P = (n - 1 + HB_NB - 1) / HB_NB;
+  std::vector<cplx> Y((size_t)n * HB_NB), T((size_t)P * HB_NB * HB_NB), Yp((size_t)n * HB_CHUNKS), W((size_t)n * HB_NB);
+  std::vector<cplx> sb(n), sw(HB_NB), st(HB_NB), sv(n);
+  std::vector<double> smem(GemmCfg<64, 64>::smem_bytes / sizeof(double));
+  int ilohi[2] = {ilo, ihi};
+  HessBatch hb{A, (size_t)n * n, n, ilohi, tau, Y.data(), T.data(), Yp.data(), W.data(), P};
+  const int tiles = (n + 63) / 64;
+  for (int p = 0; p < P; ++p) {
+    for (int j = 0; j < HB_NB; ++j) {
+      cta_hb_panel_step(c, hb, 0, p, j, red.data(), sb.data(), sw.data(), st.data());
+      for (int rt = 0; rt * HB_GEMV_ROWS < n; ++rt)
+        for (int ch = 0; ch < HB_CHUNKS; ++ch) cta_hb_gemv(c, hb, 0, p, j, rt, ch, sv.data());
+    }
+    cta_hb_panel_step(c, hb, 0, p, HB_NB, red.data(), sb.data(), sw.data(), st.data());
+    for (int ti = 0; ti < tiles; ++ti) cta_hb_gemm<HB_YTOP, false>(c, hb, 0, p, ti, 0, smem.data());
+    for (int r = 0; r < n; ++r) cta_hb_ytop_T(c, hb, 0, p, r);
+    for (int ti = 0; ti < tiles; ++ti)
+      for (int tj = 0; tj < tiles; ++tj) cta_hb_gemm<HB_RIGHT_TRAIL, false>(c, hb, 0, p, ti, tj, smem.data());
+    for (int ti = 0; ti < tiles; ++ti) cta_hb_gemm<HB_RIGHT_PANEL, false>(c, hb, 0, p, ti, 0, smem.data());
+    for (int tj = 0; tj < tiles; ++tj) cta_hb_gemm<HB_LEFT_W, false>(c, hb, 0, p, 0, tj, smem.data());
+    {
+      const int k = ilo + p * HB_NB;
+      if (k < ihi)
+        for (int j = 0; j < n - (k + HB_NB); ++j) cta_hb_w_T(c, T.data() + (size_t)p * HB_NB * HB_NB, W.data(), n - (k + HB_NB), j, true);
+    }
+    for (int ti = 0; ti < tiles; ++ti)
+      for (int tj = 0; tj < tiles; ++tj) cta_hb_gemm<HB_LEFT_UPD, false>(c, hb, 0, p, ti, tj, smem.data());
+  }
+  if (Tout) std::memcpy(Tout, T.data(), sizeof(cplx) * T.size());
+  return P;
+}

@@ -214,3 +214,31 @@ def test_full_pipeline_structured_matrices():
         assert eigpair_residuals(A, w, V).max() < 1e-12
         _, d = match_spectra(np.linalg.eigvals(A), w)
         assert d.max() < 1e-9
+
+
+def emu_hess_blocked(A, ilo, ihi):
+    n = A.shape[0]
+    Ac = np.ascontiguousarray(A.T)
+    tau = np.empty(n, dtype=np.complex128)
+    P = (n - 1 + 31) // 32
+    T = np.zeros((P, 32, 32), dtype=np.complex128)
+    emu().emu_hess_blocked(cptr(Ac), n, ilo, ihi, cptr(tau), cptr(T))
+    return Ac.T.copy(), tau, T.transpose(0, 2, 1)
+
+
+@pytest.mark.parametrize("n,ilo,ihi", [(40, 0, 39), (100, 0, 99), (97, 3, 90), (70, 0, 33), (33, 0, 32), (150, 5, 149)])
+def test_hess_blocked_matches_zgehrd(n, ilo, ihi):
+    """Same recurrences as LAPACK's blocked ZGEHRD -> H, the reflectors and tau agree to rounding."""
+    A = _rand(n, 50 + n)
+    A[ihi + 1:, :ihi + 1] = 0          # what ZGEBAL's permutation leaves: upper triangular outside [ilo, ihi]
+    A[:, :ilo] = np.triu(A[:, :ilo])
+    A[ihi + 1:, ihi + 1:] = np.triu(A[ihi + 1:, ihi + 1:])
+    Hh, tau, T = emu_hess_blocked(A, ilo, ihi)
+    ref, rtau, info = lapack.zgehrd(np.asfortranarray(A), lo=ilo, hi=ihi)
+    assert info == 0
+    q, info = lapack.zunghr(np.asfortranarray(Hh), tau[:-1], lo=ilo, hi=ihi)
+    H = np.triu(Hh, -1)
+    assert np.abs(q.conj().T @ q - np.eye(n)).max() < 1e-13
+    assert np.abs(q @ H @ q.conj().T - A).max() < 1e-13 * n * np.abs(A).max()
+    assert np.abs(Hh - ref).max() < 1e-11 * np.abs(A).max()
+    assert np.abs(tau[:-1] - rtau).max() < 1e-11

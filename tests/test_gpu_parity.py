@@ -71,6 +71,28 @@ def test_balance_bitwise_and_hessenberg_similarity():
         assert np.abs(q @ H @ q.conj().T - ba).max() < 1e-13 * n * np.abs(ba).max()
 
 
+@pytest.mark.parametrize("mode", [1, 2, 0])
+@pytest.mark.parametrize("n", [33, 97, 320, 640])
+def test_hessenberg_matches_zgehrd(n, mode):
+    """Stage 3b against LAPACK's ZGEHRD on the same balanced matrix: H, the reflectors and tau agree to
+    rounding (mode 1: batched blocked + DMMA tensor-core updates, 2: same with scalar GEMM, 0: v1 unblocked)."""
+    from scipy.linalg import lapack
+    A = _rand(n, 900 + n)[0]
+    A[5, :] = 0; A[:, 11] = 0                  # make ZGEBAL isolate something: ilo > 0 or ihi < n-1
+    sb.set_hess_mode(mode)
+    try:
+        bal, scale, ilo, ihi, Hh, tau = sb.debug_stages(A)
+    finally:
+        sb.set_hess_mode(1)
+    ba, lo, hi, sc, info = lapack.zgebal(np.asfortranarray(A), scale=1, permute=1)
+    assert (ilo, ihi) == (lo, hi) and np.array_equal(bal, ba)
+    ref, rtau, info = lapack.zgehrd(ba, lo=lo, hi=hi)
+    scale_ = np.abs(ba).max()
+    assert np.abs(np.triu(Hh, -1) - np.triu(ref, -1)).max() < 1e-11 * scale_ * np.sqrt(n)
+    assert np.abs(Hh - ref).max() < 1e-10 * scale_ * np.sqrt(n)
+    assert np.abs(tau[:-1] - rtau).max() < 1e-10
+
+
 # ---- stages 3-6 on caller-supplied matrices (config Cr) ----------------------------------------
 @pytest.mark.parametrize("n,batch", [(8, 3), (64, 4), (200, 3), (320, 2)])
 def test_zgeev_batch_random(n, batch):
