@@ -53,6 +53,8 @@ int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_th
 /* Hessenberg stage variant: 1 (default) batched blocked reduction with DMMA tensor-core updates; 2 the same with a
  * scalar-FMA GEMM (validation of the tensor-core path); 0 the unblocked one-CTA-per-matrix kernel of v1 */
 int stabgpu_set_hess_mode(int mode);
+/* eigenvector stage variant: 1 (default) register-resident inverse iteration + tensor-core back-transformation; 0 the v1 warp kernel */
+int stabgpu_set_evec_mode(int mode);
 
 /* ---- host-side pieces of the path (pure C++, no device) ------------------------------------------ */
 void stabgpu_params_default(stabgpu_params* p);                       /* stuff.f90 initial values */

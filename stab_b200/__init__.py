@@ -25,6 +25,7 @@ from .binding import (  # noqa: F401
     read_profile,
     set_tuning,
     set_hess_mode,
+    set_evec_mode,
     sgengrid,
     shard_range,
     spatial_assemble,

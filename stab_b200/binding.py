@@ -74,6 +74,7 @@ def lib():
     proto("stabgpu_device_info", i, [cp, i, _ip, _dp])
     proto("stabgpu_set_tuning", i, [i, i, i, i])
     proto("stabgpu_set_hess_mode", i, [i])
+    proto("stabgpu_set_evec_mode", i, [i])
     proto("stabgpu_params_default", None, [_pp])
     proto("stabgpu_edge_properties", i, [_pp, d])
     proto("stabgpu_sgengrid", i, [i, d, d, vp, vp, vp, vp])
@@ -239,6 +240,10 @@ def set_tuning(qr_window=0, qr_shifts=0, qr_threads=0, hess_threads=0):
 
 def set_hess_mode(mode: int):
     lib().stabgpu_set_hess_mode(int(mode))
+
+
+def set_evec_mode(mode: int):
+    lib().stabgpu_set_evec_mode(int(mode))
 
 
 def _grid_args(p: Params, vm, g2vm, g22vm, deta, d2eta):

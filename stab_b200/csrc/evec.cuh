@@ -179,7 +179,7 @@ SD_DEV void warp_scale_maxabs(const Cta& w, int nrows, cplx* x) {
 //         cond(H22 - lam I) * eps garbage in the decoupled trailing part.
 SD_DEV int warp_eigvec(const Cta& w, const cplx* Hh, int n, int ldh, int ilo, int ihi, const cplx* tau,
                        const double* scale, cplx lam, int kr, double hnorm, int scale_rows, cplx* c, cplx* y,
-                       unsigned char* flag, cplx* out) {
+                       unsigned char* flag, cplx* out, bool raw = false) {
   const int m = kr + 1;
   const double smlnum = SD_SAFMIN * ((double)n / SD_ULP);
   const double eps3 = fmax(SD_ULP * hnorm, smlnum);
@@ -202,10 +202,12 @@ SD_DEV int warp_eigvec(const Cta& w, const cplx* Hh, int n, int ldh, int ilo, in
   }
   for (int r = m + w.lane; r < n; r += w.ws) y[r] = mk(0.0, 0.0);
   warp_sync();
-  warp_apply_q(w, Hh, ldh, ilo, ihi, tau, y);
-  warp_gebak(w, n, ilo, ihi, scale, y);
-  warp_normalize_zgeev(w, n, y);
-  if (scale_rows > 0) warp_scale_maxabs(w, scale_rows, y);
+  if (!raw) {                                 // raw: leave the vector in the Hessenberg basis (GEMM back-transformation follows)
+    warp_apply_q(w, Hh, ldh, ilo, ihi, tau, y);
+    warp_gebak(w, n, ilo, ihi, scale, y);
+    warp_normalize_zgeev(w, n, y);
+    if (scale_rows > 0) warp_scale_maxabs(w, scale_rows, y);
+  }
   for (int r = w.lane; r < n; r += w.ws) out[r] = y[r];
   warp_sync();
   return bad;

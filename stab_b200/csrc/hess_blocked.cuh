@@ -227,6 +227,32 @@ SD_DEV void cta_hb_gemm(const Cta& c, const HessBatch& hb, int mat, int panel, i
   }
 }
 
+// ---- back-transformation of the eigenvectors: X <- Q X, Q = Q_0 Q_1 ... (ZUNMHR), one panel ----
+// X(k+1:ihi+1, :) -= V (T (V^H X(k+1:ihi+1, :))) for panels in DECREASING order.
+enum BtPhase { BT_W = 0, BT_UPD = 1 };
+template <int PHASE, bool USE_MMA>
+SD_DEV void cta_bt_gemm(const Cta& c, const HessBatch& hb, cplx* Xall, size_t xstride, int mat, int panel, int ti, int tj, double* smem) {
+  const int n = hb.n, lda = n;
+  const cplx* A = hb.A + (size_t)mat * hb.astride;
+  cplx* X = Xall + (size_t)mat * xstride;
+  const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
+  const int k = ilo + panel * HB_NB;
+  if (k >= ihi) return;
+  cplx* W = hb.W + (size_t)mat * n * HB_NB;
+  if (PHASE == BT_W) {
+    if (ti > 0 || tj * 64 >= n) return;
+    OpL_VH L{VBlock{A, lda, k, ihi, k + 1}};
+    OpR_ColMajor R{X + (k + 1), n};
+    cta_gemm_tile<32, 64, false, USE_MMA>(c, smem, 0, tj * 64, HB_NB, n, ihi - k, L, R, W, HB_NB);
+  } else {
+    const int m = ihi - k;
+    if (ti * 64 >= m || tj * 64 >= n) return;
+    OpL_V L{VBlock{A, lda, k, ihi, k + 1}};
+    OpR_ColMajor R{W, HB_NB};
+    cta_gemm_tile<64, 64, true, USE_MMA>(c, smem, ti * 64, tj * 64, m, n, HB_NB, L, R, X + (k + 1), n);
+  }
+}
+
 // Y(0:k+1, :) *= T  (upper triangular, right multiplication); thread per row
 SD_DEV void cta_hb_ytop_T(const Cta& c, const HessBatch& hb, int mat, int panel, int rowblock) {
   const int n = hb.n;

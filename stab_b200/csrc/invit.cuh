@@ -1,0 +1,181 @@
+// invit.cuh -- right eigenvectors of the Hessenberg matrix by shift-invert inverse iteration,
+// register-resident variant (GPU only).  Stage (4)/(6) of the pipeline: replaces ZTREVC of the
+// ZGEEV('N','V') the reference calls (temporal.f90:803, spatial.f90:1043) by the ZHSEIN/ZLAEIN
+// idea -- one solve with (H - lambda I) per eigenvalue, started from a vector of size eps.
+//
+// One WARP per eigenvalue, 8 eigenvalues per CTA advancing in lock step through the elimination
+//   for k = m-1 .. 1:  combine Hessenberg column k-1 with the carried column (column operations
+//                      from the bottom row up, with column interchanges -- see evec.cuh)
+// * the carried column c and the right-hand side y live in REGISTERS: lane l owns rows
+//   r = 32 s + l (s = 0..NS-1), so every update is two complex FMAs on registers;
+// * the Hessenberg columns are staged ONCE per CTA through shared memory in double-buffered
+//   8-column blocks with cp.async (LDGSTS), shared by the 8 warps: global/L2 traffic is
+//   (n^2/2 * 16 B) per 8 eigenvalues instead of per eigenvalue;
+// * the pivots travel by warp shuffles; the multipliers overwrite the dead entries of c.
+// The vectors come out in the Hessenberg basis (zero below the diagonal block's end kr);
+// the back-transformation by Q is a tensor-core GEMM (k_bt_* kernels), then k_vec_finalize.
+#pragma once
+#include "common.cuh"
+
+#ifndef STAB_EMU
+namespace stab {
+
+constexpr int INVIT_WARPS = 8;
+constexpr int INVIT_CB = 8;        // columns per staged block
+
+SD_DEV void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+SD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+SD_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+SD_DEV cplx shfl_c(cplx v, int src) { return mk(__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)); }
+
+// grid: (ceil(n / (8*rounds)), batch), block 256.  smem: 2 * INVIT_CB * n complex.
+template <int NS>
+__global__ void __launch_bounds__(INVIT_WARPS * 32, 1)
+k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restrict__ lam, const int* __restrict__ kr,
+        const double* __restrict__ hnorm, cplx* __restrict__ Y, size_t ystride, int* __restrict__ bad, int rounds) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* sH = reinterpret_cast<cplx*>(smem_raw);            // [2][INVIT_CB][n]
+  const int p = blockIdx.y;
+  const cplx* H = Hh + (size_t)p * hstride;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const double smlnum = SD_SAFMIN * ((double)n / SD_ULP);
+  const double eps3 = fmax(SD_ULP * hnorm[p], smlnum);
+  const double growto = 0.1 / sqrt((double)n);
+  const int nblk = (n - 1 + INVIT_CB - 1) / INVIT_CB;      // blocks of steps k = n-1 .. 1
+
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int e = (blockIdx.x * rounds + rd) * INVIT_WARPS + wid;
+    const bool live = e < n;
+    const int m = live ? kr[(size_t)p * n + e] + 1 : 0;     // leading block order
+    const cplx lm = live ? lam[(size_t)p * n + e] : mk(0.0, 0.0);
+    cplx c[NS], y[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { c[s] = mk(0.0, 0.0); y[s] = mk(0.0, 0.0); }
+    unsigned flags = 0u;
+    cplx cdiag = mk(0.0, 0.0), ydiag = mk(0.0, 0.0);
+
+    // block b covers steps k = kb .. max(kb-CB+1, 1), i.e. columns kb-1 .. ; rows 0..kb of each
+    auto prefetch = [&](int b, int buf) {
+      const int kb = n - 1 - b * INVIT_CB;
+      cplx* dst = sH + (size_t)buf * INVIT_CB * n;
+      for (int q = 0; q < INVIT_CB; ++q) {
+        const int col = kb - 1 - q;
+        if (col < 0) break;
+        const cplx* src = H + (size_t)col * n;
+        for (int r = threadIdx.x; r <= col + 1; r += blockDim.x) cp_async16(dst + (size_t)q * n + r, src + r);
+      }
+      cp_async_commit();
+    };
+    __syncthreads();                                        // previous round finished with both buffers
+    prefetch(0, 0);
+    for (int b = 0; b < nblk; ++b) {
+      const int buf = b & 1;
+      cp_async_wait<0>();
+      __syncthreads();                                      // block b landed; everyone left block b-1
+      if (b + 1 < nblk) prefetch(b + 1, buf ^ 1);
+      const cplx* tile = sH + (size_t)buf * INVIT_CB * n;
+      const int kb = n - 1 - b * INVIT_CB;
+      for (int q = 0; q < INVIT_CB; ++q) {
+        const int k = kb - q;
+        if (k < 1) break;
+        if (!live || k > m - 1) continue;
+        if (k == m - 1) {                                   // start: carried column = column m-1 of H - lam I
+          const cplx* hc = H + (size_t)(m - 1) * n;
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            const int r = 32 * s + lane;
+            if (r < m) {
+              cplx a = hc[r];
+              if (r == m - 1) a -= lm;
+              c[s] = a; y[s] = mk(eps3, 0.0);
+            }
+          }
+          cdiag = hc[m - 1] - lm;
+          ydiag = mk(eps3, 0.0);
+        }
+        const cplx* acol = tile + (size_t)q * n;            // column k-1
+        const cplx ak = acol[k];
+        const bool sw = cabs1(ak) > cabs1(cdiag);
+        cplx piv = sw ? ak : cdiag;
+        if (is_zero(piv)) piv = mk(eps3, 0.0);
+        const cplx yk = cdiv(ydiag, piv);
+        const cplx mq = cdiv(sw ? cdiag : ak, piv);
+        cplx cnext = mk(0.0, 0.0), ynext = mk(0.0, 0.0);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if (32 * s <= k) {
+            const int r = 32 * s + lane;
+            if (r < k) {
+              cplx a = acol[r];
+              if (r == k - 1) a -= lm;
+              const cplx cr = c[s];
+              const cplx u = sw ? a : cr;
+              const cplx cn = sw ? (cr - mq * a) : (a - mq * cr);
+              const cplx yn = y[s] - yk * u;
+              c[s] = cn; y[s] = yn;
+              if (r == k - 1) { cnext = cn; ynext = yn; }
+            } else if (r == k) {
+              c[s] = mq; y[s] = yk;
+              if (sw) flags |= (1u << s);
+            }
+          }
+        }
+        cdiag = shfl_c(cnext, (k - 1) & 31);
+        ydiag = shfl_c(ynext, (k - 1) & 31);
+      }
+    }
+    // ---- k = 0, then x = T_{m-1} ... T_1 y (forward recurrence carried by shuffles) ----
+    int isbad = 0;
+    if (live) {
+      if (m == 1) { cdiag = H[0] - lm; ydiag = mk(eps3, 0.0); }
+      cplx piv = cdiag;
+      if (is_zero(piv)) piv = mk(eps3, 0.0);
+      cplx prev = cdiv(ydiag, piv);                         // current value of y[k-1]
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (32 * s < m) {
+          const unsigned fl_s = flags;                      // each lane's own flag word
+          for (int i = (s == 0 ? 1 : 0); i < 32 && 32 * s + i < m; ++i) {
+            const cplx yk_in = shfl_c(y[s], i);
+            const cplx mk_ = shfl_c(c[s], i);
+            const unsigned fl = __shfl_sync(0xffffffffu, fl_s, i);
+            const cplx t = yk_in - mk_ * prev;
+            const bool f = (fl >> s) & 1u;
+            const cplx fin = f ? t : prev;                  // final x[k-1]
+            prev = f ? prev : t;
+            if (i > 0) { if (lane == i - 1) y[s] = fin; }
+            else { if (lane == 31) y[s > 0 ? s - 1 : 0] = fin; }
+          }
+        }
+      }
+      // last row m-1 gets the carried value
+      {
+        const int rl = m - 1;
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (32 * s + lane == rl) y[s] = prev;
+      }
+      double vn = 0.0;
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (32 * s + lane < m) vn += cabs1(y[s]);
+      vn = warp_sum(vn);
+      if (!(vn == vn) || vn > 1.0e300 || vn < growto) isbad = 1;
+      cplx* out = Y + (size_t)p * ystride + (size_t)e * n;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int r = 32 * s + lane;
+        if (r < n) out[r] = (r < m) ? y[s] : mk(0.0, 0.0);
+      }
+      if (lane == 0) bad[(size_t)p * n + e] = isbad;
+    }
+  }
+}
+
+}  // namespace stab
+#endif

@@ -10,6 +10,7 @@
 #include "evec.cuh"
 #include "lu.cuh"
 #include "hess_blocked.cuh"
+#include "invit.cuh"
 
 namespace stab {
 
@@ -338,7 +339,8 @@ __global__ void k_sort(const cplx* w, int n, int mode, const double* hnorm, cons
 // ---- stage 6: eigenvectors ----------------------------------------------------------------------
 // grid (chunks, batch); each warp takes eigen-indices e = chunk*warps + wid, += chunks*warps
 __global__ void k_evec(const cplx* Hh, size_t hstride, int n, const int* ilohi, const cplx* tau, const double* scale,
-                       const cplx* lam, const int* kr, const double* hnorm, int scale_rows, cplx* V, size_t vstride, int* vinfo) {
+                       const cplx* lam, const int* kr, const double* hnorm, int scale_rows, cplx* V, size_t vstride, int* vinfo,
+                       const int* badsel, int raw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta w = make_cta(nullptr);
   const int p = blockIdx.y;
@@ -348,11 +350,47 @@ __global__ void k_evec(const cplx* Hh, size_t hstride, int n, const int* ilohi, 
   const int ilo = ilohi[2 * p], ihi = ilohi[2 * p + 1];
   int bad = 0;
   for (int e = blockIdx.x * w.nw + w.wid; e < n; e += gridDim.x * w.nw) {
+    if (badsel && badsel[(size_t)p * n + e] == 0) continue;     // fallback pass: only vectors the fast kernel rejected
     bad += warp_eigvec(w, Hh + (size_t)p * hstride, n, n, ilo, ihi, tau + (size_t)p * n, scale + (size_t)p * n,
                        lam[(size_t)p * n + e], kr[(size_t)p * n + e], hnorm[p], scale_rows, cvec, yvec, flag,
-                       V + (size_t)p * vstride + (size_t)e * n);
+                       V + (size_t)p * vstride + (size_t)e * n, raw != 0);
   }
   if (bad && w.lane == 0) atomicAdd(vinfo + p, bad);
+}
+
+// back-transformation GEMM phases (hess_blocked.cuh) and the T multiply
+template <int PHASE, bool USE_MMA>
+__global__ void __launch_bounds__(GEMM_THREADS) k_bt_gemm(HessBatch hb, cplx* X, size_t xstride, int panel) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta c = make_cta(nullptr);
+  cta_bt_gemm<PHASE, USE_MMA>(c, hb, X, xstride, blockIdx.z, panel, blockIdx.x, blockIdx.y, reinterpret_cast<double*>(smem_raw));
+}
+
+__global__ void k_bt_w_T(HessBatch hb, int panel) {
+  Cta c = make_cta(nullptr);
+  const int mat = blockIdx.y, n = hb.n;
+  const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
+  if (ilo + panel * HB_NB >= ihi) return;
+  cta_hb_w_T(c, hb.T + ((size_t)mat * hb.P + panel) * HB_NB * HB_NB, hb.W + (size_t)mat * n * HB_NB, n, blockIdx.x, false);
+}
+
+// ZGEBAK + ZGEEV normalisation [+ temporal.f90:867-879 scaling] of every column; warp per column
+__global__ void k_vec_finalize(cplx* V, size_t vstride, int n, const int* ilohi, const double* scale, int scale_rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta w = make_cta(nullptr);
+  const int p = blockIdx.y;
+  cplx* x = reinterpret_cast<cplx*>(smem_raw) + (size_t)w.wid * n;
+  const int ilo = ilohi[2 * p], ihi = ilohi[2 * p + 1];
+  for (int e = blockIdx.x * w.nw + w.wid; e < n; e += gridDim.x * w.nw) {
+    cplx* col = V + (size_t)p * vstride + (size_t)e * n;
+    for (int r = w.lane; r < n; r += 32) x[r] = col[r];
+    __syncwarp();
+    warp_gebak(w, n, ilo, ihi, scale + (size_t)p * n, x);
+    warp_normalize_zgeev(w, n, x);
+    if (scale_rows > 0) warp_scale_maxabs(w, scale_rows, x);
+    for (int r = w.lane; r < n; r += 32) col[r] = x[r];
+    __syncwarp();
+  }
 }
 
 }  // namespace stab

@@ -16,7 +16,7 @@ namespace {
 thread_local std::string g_err;
 int g_device = -1;
 bool g_inited = false;
-struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
+struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
 
@@ -96,7 +96,7 @@ struct stabgpu_plan {
   DBuf<cplx> hbY, hbT, hbYp, hbW;      // blocked Hessenberg workspaces
   int hbP = 0;
   DBuf<double> scale, hnorm;
-  DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr;
+  DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr, vbad;
   cudaEvent_t ev[ST_N + 1] = {};
   float ms[ST_N] = {};
   long long launches = 0;
@@ -141,7 +141,7 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
   if (pl->want_vectors && (pl->Hq.alloc((size_t)cap * N * N) || pl->V.alloc((size_t)cap * N * N))) return 1;
   if (pl->tau.alloc((size_t)cap * N) || pl->w.alloc((size_t)cap * N) || pl->eig.alloc((size_t)cap * N) || pl->lam.alloc((size_t)cap * N)) return 1;
   if (pl->scale.alloc((size_t)cap * N) || pl->hnorm.alloc(cap) || pl->cnt.alloc((size_t)cap * N)) return 1;
-  if (pl->blkend.alloc((size_t)cap * N) || pl->kr.alloc((size_t)cap * N)) return 1;
+  if (pl->blkend.alloc((size_t)cap * N) || pl->kr.alloc((size_t)cap * N) || pl->vbad.alloc((size_t)cap * N)) return 1;
   pl->hbP = (N - 1 + HB_NB - 1) / HB_NB;
   if (pl->hbY.alloc((size_t)cap * N * HB_NB) || pl->hbT.alloc((size_t)cap * pl->hbP * HB_NB * HB_NB) ||
       pl->hbYp.alloc((size_t)cap * N * HB_CHUNKS) || pl->hbW.alloc((size_t)cap * N * HB_NB)) return 1;
@@ -218,6 +218,88 @@ int run_hessenberg(stabgpu_plan* pl) {
   return 0;
 }
 
+template <int PHASE>
+int launch_bt_gemm(stabgpu_plan* pl, const HessBatch& hb, int panel, int ti, int tj, size_t smem) {
+  dim3 grid(ti, tj, pl->npts);
+  CU(cudaFuncSetAttribute(k_bt_gemm<PHASE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bt_gemm<PHASE, true><<<grid, GEMM_THREADS, smem, pl->stream>>>(hb, pl->V.p, (size_t)pl->N * pl->N, panel);
+  CU(cudaGetLastError());
+  pl->launches += 1;
+  return 0;
+}
+
+template <int NS>
+int launch_invit(stabgpu_plan* pl, int rounds) {
+  const int N = pl->N, np = pl->npts;
+  const size_t st = (size_t)N * N;
+  const size_t sm = 2 * (size_t)INVIT_CB * N * sizeof(cplx);
+  CU(cudaFuncSetAttribute(k_invit<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid((N + INVIT_WARPS * rounds - 1) / (INVIT_WARPS * rounds), np);
+  k_invit<NS><<<grid, INVIT_WARPS * 32, sm, pl->stream>>>(pl->A.p, st, N, pl->lam.p, pl->kr.p, pl->hnorm.p, pl->V.p, st, pl->vbad.p, rounds);
+  CU(cudaGetLastError());
+  pl->launches += 1;
+  return 0;
+}
+
+// Stage 6: right eigenvectors.  evec_mode 1 (default, N <= 640 and blocked Hessenberg factors available):
+// register-resident inverse iteration -> GEMM back-transformation -> finalize; otherwise the v1 warp kernel.
+int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
+  const int N = pl->N, np = pl->npts;
+  const size_t st = (size_t)N * N;
+  cudaStream_t s = pl->stream;
+  CU(cudaMemsetAsync(pl->info_v.p, 0, sizeof(int) * np, s));
+  int warps = 8;
+  const size_t per_warp = 2 * (size_t)N * sizeof(cplx) + (size_t)N;
+  while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+  const size_t sm_old = warps * per_warp;
+  if (sm_old > 227 * 1024) return fail("libstabgpu: matrix too large for the eigenvector kernel");
+  CU(cudaFuncSetAttribute(k_evec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_old));
+  int chunks = 1;
+  while (chunks * np < 2 * 148 && chunks * warps < N) chunks *= 2;
+  dim3 grid_old(chunks, np);
+  const bool fast = g_tune.evec_mode == 1 && g_tune.hess_mode != 0 && N <= 640;
+  if (!fast) {
+    // the reflectors live in A (ZGEHRD layout); the QR ran on the copy Hq
+    k_evec<<<grid_old, warps * 32, sm_old, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->scale.p, pl->lam.p, pl->kr.p, pl->hnorm.p,
+                                                scale_rows, pl->V.p, st, pl->info_v.p, nullptr, 0);
+    CU(cudaGetLastError());
+    pl->launches += 1;
+    return 0;
+  }
+  const int rounds = 4;
+  int rc;
+  if (N <= 160) rc = launch_invit<5>(pl, rounds);
+  else if (N <= 320) rc = launch_invit<10>(pl, rounds);
+  else if (N <= 480) rc = launch_invit<15>(pl, rounds);
+  else rc = launch_invit<20>(pl, rounds);
+  if (rc) return 1;
+  // vectors the fast kernel rejected (no growth / overflow): ZLAEIN's retry vectors, v1 kernel, Hessenberg basis
+  k_evec<<<grid_old, warps * 32, sm_old, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->scale.p, pl->lam.p, pl->kr.p, pl->hnorm.p,
+                                              0, pl->V.p, st, pl->info_v.p, pl->vbad.p, 1);
+  CU(cudaGetLastError());
+  pl->launches += 1;
+  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP};
+  const int tn = (N + 63) / 64;
+  for (int p = pl->hbP - 1; p >= 0; --p) {
+    const int rows_max = N - 1 - p * HB_NB;
+    if (rows_max <= 0) continue;
+    if (launch_bt_gemm<BT_W>(pl, hb, p, 1, tn, GemmCfg<32, 64>::smem_bytes)) return 1;
+    k_bt_w_T<<<dim3((N + 127) / 128, np), 128, 0, s>>>(hb, p);
+    pl->launches += 1;
+    if (launch_bt_gemm<BT_UPD>(pl, hb, p, (rows_max + 63) / 64, tn, GemmCfg<64, 64>::smem_bytes)) return 1;
+  }
+  {
+    const size_t smf = 8 * (size_t)N * sizeof(cplx);
+    CU(cudaFuncSetAttribute(k_vec_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+    int ch = 1;
+    while (ch * np < 4 * 148 && ch * 8 < N) ch *= 2;
+    k_vec_finalize<<<dim3(ch, np), 256, smf, s>>>(pl->V.p, st, N, pl->ilohi.p, pl->scale.p, scale_rows);
+    CU(cudaGetLastError());
+    pl->launches += 1;
+  }
+  return 0;
+}
+
 // the eigen-pipeline on pl->A (npts matrices of order N): balance -> Hessenberg -> QR -> sort [-> vectors]
 int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   const int N = pl->N, np = pl->npts;
@@ -246,23 +328,7 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(pl->ev[ST_SORT + 1], s));
   pl->launches += 4;
-  if (pl->want_vectors) {
-    CU(cudaMemsetAsync(pl->info_v.p, 0, sizeof(int) * np, s));
-    int warps = 8;
-    const size_t per_warp = 2 * (size_t)N * sizeof(cplx) + (size_t)N;
-    while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
-    size_t sm = warps * per_warp;
-    if (sm > 227 * 1024) return fail("libstabgpu: matrix too large for the eigenvector kernel");
-    CU(cudaFuncSetAttribute(k_evec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    int chunks = 1;
-    while (chunks * np < 2 * 148 && chunks * warps < N) chunks *= 2;
-    dim3 grid(chunks, np);
-    // the reflectors live in A (ZGEHRD layout); the QR ran on the copy Hq
-    k_evec<<<grid, warps * 32, sm, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->scale.p, pl->lam.p, pl->kr.p, pl->hnorm.p,
-                                        scale_rows, pl->V.p, st, pl->info_v.p);
-    CU(cudaGetLastError());
-    pl->launches += 1;
-  }
+  if (pl->want_vectors && run_eigvecs(pl, scale_rows)) return 1;
   CU(cudaEventRecord(pl->ev[ST_EVEC + 1], s));
   return 0;
 }
@@ -338,6 +404,7 @@ int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb)
 }
 
 int stabgpu_set_hess_mode(int mode) { g_tune.hess_mode = mode; return 0; }
+int stabgpu_set_evec_mode(int mode) { g_tune.evec_mode = mode; return 0; }
 
 int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads) {
   if (qr_window > 0) g_tune.W = qr_window;

@@ -112,6 +112,20 @@ def test_zgeev_batch_random(n, batch):
         assert d.max() < 1e-11 * np.abs(w[b]).max()
 
 
+def test_eigenvector_paths_agree():
+    """Register-resident inverse iteration + tensor-core back-transformation (default) against the v1
+    warp kernel (per-vector reflector application): same vectors to rounding."""
+    A = _rand(200, 77, 2)
+    w1, V1, i1 = sb.zgeev_batch(A, want_vectors=True)
+    sb.set_evec_mode(0)
+    try:
+        w0, V0, i0 = sb.zgeev_batch(A, want_vectors=True)
+    finally:
+        sb.set_evec_mode(1)
+    assert np.array_equal(w0, w1)
+    assert np.abs(V0 - V1).max() < 1e-10
+
+
 def test_zgeev_batch_structured():
     """Matrices with isolated eigenvalues (balancing permutes), defective blocks and zero rows."""
     n = 40
