@@ -57,6 +57,11 @@ SD_HD void fma_acc_conj(cplx& acc, cplx a, cplx b) {
   acc.re = fma(a.re, b.re, acc.re); acc.re = fma(a.im, b.im, acc.re);
   acc.im = fma(a.re, b.im, acc.im); acc.im = fma(-a.im, b.re, acc.im);
 }
+// acc -= a*b  (four FMAs)
+SD_HD void fms_acc(cplx& acc, cplx a, cplx b) {
+  acc.re = fma(-a.re, b.re, acc.re); acc.re = fma(a.im, b.im, acc.re);
+  acc.im = fma(-a.re, b.im, acc.im); acc.im = fma(-a.im, b.re, acc.im);
+}
 // robust complex division (Smith), as LAPACK ZLADIV in spirit
 SD_HD cplx cdiv(cplx a, cplx b) {
   if (fabs(b.im) <= fabs(b.re)) {

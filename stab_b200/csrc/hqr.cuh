@@ -226,7 +226,18 @@ struct HqrSmem {
   cplx* shifts;  // ns_max
   cplx* sm;      // ns_max * (ns_max + 1)   trailing block for the shift computation
   SmallCtl* ctl;
+  long long* prof;   // optional cycle counters (debug): scan, shifts, window io, chase, left slab, right slab, small blocks, #sweeps, #passes
 };
+
+#if defined(STAB_EMU)
+#define HQR_PROF_START()
+#define HQR_PROF(i)
+#define HQR_COUNT(i)
+#else
+#define HQR_PROF_START() long long pt0_ = (sh.prof && c.tid == 0) ? clock64() : 0
+#define HQR_PROF(i) do { if (sh.prof && c.tid == 0) { long long t1_ = clock64(); sh.prof[i] += t1_ - pt0_; pt0_ = t1_; } } while (0)
+#define HQR_COUNT(i) do { if (sh.prof && c.tid == 0) sh.prof[i] += 1; } while (0)
+#endif
 
 // One multishift sweep over the active block [L, I] of the global Hessenberg matrix H.
 SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, int L, int I, int ns) {
@@ -234,7 +245,10 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
   const int W = sh.W, ldw = sh.ldw;
   const int T = I - L + 2 * ns - 2;
   int ta = 0;
+  HQR_PROF_START();
+  HQR_COUNT(7);
   while (ta < T) {
+    HQR_COUNT(8);
     int tb, g0;
     if (ta == 0) {
       int first = W - 2; if (first > sh.steps_max) first = sh.steps_max;
@@ -252,11 +266,14 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
       sh.win[row + col * ldw] = (row <= col + 2) ? H[(g0 + row) + (size_t)(g0 + col) * ldh] : mk(0.0, 0.0);
     }
     cta_sync();
+    HQR_PROF(2);
     chase(g, sh.win, ldw, g0, 0, wsz - 1, L, I, sh.shifts, ns, ta, tb, sh.rec, sh.cur);
+    HQR_PROF(3);
     for (int q = c.tid; q < wsz * wsz; q += c.nt) {
       const int col = q / wsz, row = q - col * wsz;
       if (row <= col + 2) H[(g0 + row) + (size_t)(g0 + col) * ldh] = sh.win[row + col * ldw];
     }
+    HQR_PROF(2);
     const int smax = I - 1 - L;
     // left slab: rows [g0, g1], columns (g1, I]; thread per column, bulge-major with carry
     for (int col = g1 + 1 + c.tid; col <= I; col += c.nt) {
@@ -277,6 +294,8 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
         hc[k] = x;
       }
     }
+    cta_sync();
+    HQR_PROF(4);
     // right slab: rows [L, g0), columns of the chain; thread per row
     for (int row = L + c.tid; row < g0; row += c.nt) {
       cplx* hr = H + row;
@@ -297,6 +316,7 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
       }
     }
     cta_sync();
+    HQR_PROF(5);
     ta = tb;
   }
 }
@@ -317,12 +337,15 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
   const long itmax = 30L * (nh > 10 ? nh : 10);
   int info = 0;
   cta_sync();
+  HQR_PROF_START();
   while (I >= ilo) {
+    HQR_PROF(9);
     // largest k in (ilo, I] whose subdiagonal is negligible
     int best = ilo;
     for (int k = ilo + 1 + c.tid; k <= I; k += c.nt)
       if (negligible_subdiag(at, k, ilo, ihi, smlnum)) best = k;
     const int L = cta_max_i(c, best);
+    HQR_PROF(0);
     if (L > ilo && c.tid == 0) H[L + (size_t)(L - 1) * ldh] = mk(0.0, 0.0);
     if (L == I) {
       if (c.tid == 0) w[I] = H[I + (size_t)I * ldh];
@@ -342,6 +365,7 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
       if (bad) info += bad;
       I = L - 1; stagn = 0;
       cta_sync();
+      HQR_PROF(6);
       continue;
     }
     if (total++ >= itmax) { info += I - ilo + 1; for (int k = ilo + c.tid; k <= I; k += c.nt) w[k] = H[k + (size_t)k * ldh]; break; }
@@ -368,6 +392,7 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
       smem_hqr(g, sh.sm, lds, ns, sh.shifts, sh.ctl, sh.cur);
       cta_sync();
     }
+    HQR_PROF(1);
     sweep_multishift(c, sh, H, ldh, L, I, ns);
   }
   cta_sync();

@@ -33,7 +33,105 @@ SD_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N))
 
 SD_DEV cplx shfl_c(cplx v, int src) { return mk(__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)); }
 
-// grid: (ceil(n / (8*rounds)), batch), block 256.  smem: 2 * INVIT_CB * n complex.
+// One elimination step k with the boundary slot index SB = k >> 5 known at compile time: rows < 32*SB
+// (slots 0..SB-1, or 0..SB-2 when k is a multiple of 32) are updated branch-free on registers.
+template <int NS, int SB>
+SD_DEV void invit_step(int k, int lane, const cplx* __restrict__ acol, cplx lm, double eps3, cplx (&c)[NS], cplx (&y)[NS],
+                       unsigned& flags, cplx& cdiag, cplx& ydiag) {
+  const cplx ak = acol[k];
+  const bool sw = cabs1(ak) > cabs1(cdiag);
+  cplx piv = sw ? ak : cdiag;
+  if (is_zero(piv)) piv = mk(eps3, 0.0);
+  // 1/piv = conj(piv)/|piv|^2: pivots are O(eps3)..O(||H||), their squares are far from the
+  // overflow/underflow thresholds, so Smith's dependent divisions are not needed here
+  const double rd = __drcp_rn(fma(piv.re, piv.re, piv.im * piv.im));
+  const cplx inv = mk(piv.re * rd, -piv.im * rd);
+  const cplx yk = ydiag * inv;
+  const cplx mq = (sw ? cdiag : ak) * inv;
+  cplx cnext = mk(0.0, 0.0), ynext = mk(0.0, 0.0);
+  const bool edge = (k & 31) == 0;                   // row k-1 lives in slot SB-1 (lane 31)
+  // (1) boundary slot(s): diagonal shift, pivot capture, multiplier store
+#pragma unroll
+  for (int s = (SB > 0 ? SB - 1 : 0); s <= SB; ++s) {
+    if (s == SB || edge) {
+      const int r = 32 * s + lane;
+      if (r < k) {
+        cplx a = acol[r];
+        if (r == k - 1) a -= lm;
+        const cplx cr = c[s];
+        const cplx u = sw ? a : cr;
+        const cplx cn = sw ? (cr - mq * a) : (a - mq * cr);
+        const cplx yn = y[s] - yk * u;
+        c[s] = cn; y[s] = yn;
+        if (r == k - 1) { cnext = cn; ynext = yn; }
+      } else if (r == k) {
+        c[s] = mq; y[s] = yk;
+        if (sw) flags |= (1u << s);
+      }
+    }
+  }
+  cdiag = shfl_c(cnext, (k - 1) & 31);
+  ydiag = shfl_c(ynext, (k - 1) & 31);
+  // (2) the bulk: slots that hold only rows < k-1
+  constexpr int NP = SB > 0 ? SB - 1 : 0;            // always plain
+  if (sw) {
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+      const cplx a = acol[32 * s + lane];
+      fms_acc(y[s], yk, a); fms_acc(c[s], mq, a);
+    }
+    if (SB > 0 && !edge) {
+      const cplx a = acol[32 * (SB - 1) + lane];
+      fms_acc(y[SB > 0 ? SB - 1 : 0], yk, a); fms_acc(c[SB > 0 ? SB - 1 : 0], mq, a);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+      cplx a = acol[32 * s + lane];
+      const cplx cr = c[s];
+      fms_acc(y[s], yk, cr); fms_acc(a, mq, cr);
+      c[s] = a;
+    }
+    if (SB > 0 && !edge) {
+      cplx a = acol[32 * (SB - 1) + lane];
+      const cplx cr = c[SB > 0 ? SB - 1 : 0];
+      fms_acc(y[SB > 0 ? SB - 1 : 0], yk, cr); fms_acc(a, mq, cr);
+      c[SB > 0 ? SB - 1 : 0] = a;
+    }
+  }
+}
+
+// The 32 steps k = 32*SB+31 .. 32*SB (four staged 8-column blocks), then recurse to SB-1.
+template <int NS, int SB>
+struct InvitSlot {
+  template <class Prefetch>
+  SD_DEV static void run(int n, int m, bool live, int lane, const cplx* __restrict__ H, cplx* sH, cplx lm, double eps3,
+                         cplx (&c)[NS], cplx (&y)[NS], unsigned& flags, cplx& cdiag, cplx& ydiag, int& buf, Prefetch& prefetch) {
+    for (int bq = 3; bq >= 0; --bq) {
+      const int B = 4 * SB + bq;
+      if (8 * B > n - 1) continue;                       // block above the matrix (uniform)
+      cp_async_wait<0>();
+      __syncthreads();                                   // block B landed; everyone left block B+1
+      if (B > 0) prefetch(B - 1, buf ^ 1);
+      const cplx* tile = sH + (size_t)buf * INVIT_CB * n;
+      for (int q = INVIT_CB - 1; q >= 0; --q) {
+        const int k = 8 * B + q;
+        if (k > n - 1 || k < 1) continue;
+        if (!live || k > m - 1) continue;
+        invit_step<NS, SB>(k, lane, tile + (size_t)q * n, lm, eps3, c, y, flags, cdiag, ydiag);
+      }
+      buf ^= 1;
+    }
+    InvitSlot<NS, SB - 1>::run(n, m, live, lane, H, sH, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+  }
+};
+template <int NS>
+struct InvitSlot<NS, -1> {
+  template <class Prefetch>
+  SD_DEV static void run(int, int, bool, int, const cplx*, cplx*, cplx, double, cplx (&)[NS], cplx (&)[NS], unsigned&, cplx&, cplx&, int&, Prefetch&) {}
+};
+
+// grid: (ceil(n / (8*rounds)), batch), block 256.  smem: 2 * INVIT_CB * n complex.  n <= 32 NS.
 template <int NS>
 __global__ void __launch_bounds__(INVIT_WARPS * 32, 1)
 k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restrict__ lam, const int* __restrict__ kr,
@@ -46,7 +144,6 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
   const double smlnum = SD_SAFMIN * ((double)n / SD_ULP);
   const double eps3 = fmax(SD_ULP * hnorm[p], smlnum);
   const double growto = 0.1 / sqrt((double)n);
-  const int nblk = (n - 1 + INVIT_CB - 1) / INVIT_CB;      // blocks of steps k = n-1 .. 1
 
   for (int rd = 0; rd < rounds; ++rd) {
     const int e = (blockIdx.x * rounds + rd) * INVIT_WARPS + wid;
@@ -59,80 +156,39 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
     unsigned flags = 0u;
     cplx cdiag = mk(0.0, 0.0), ydiag = mk(0.0, 0.0);
 
-    // block b covers steps k = kb .. max(kb-CB+1, 1), i.e. columns kb-1 .. ; rows 0..kb of each
-    auto prefetch = [&](int b, int buf) {
-      const int kb = n - 1 - b * INVIT_CB;
-      cplx* dst = sH + (size_t)buf * INVIT_CB * n;
+    // block B covers steps k = 8B+7 .. 8B, i.e. columns k-1 = 8B+6 .. 8B-1, rows 0..k of each;
+    // tile column q <-> step k = 8B+q
+    auto prefetch = [&](int B, int bufi) {
+      cplx* dst = sH + (size_t)bufi * INVIT_CB * n;
       for (int q = 0; q < INVIT_CB; ++q) {
-        const int col = kb - 1 - q;
-        if (col < 0) break;
-        const cplx* src = H + (size_t)col * n;
-        for (int r = threadIdx.x; r <= col + 1; r += blockDim.x) cp_async16(dst + (size_t)q * n + r, src + r);
+        const int k = 8 * B + q;
+        if (k < 1 || k > n - 1) continue;
+        const cplx* src = H + (size_t)(k - 1) * n;
+        for (int r = threadIdx.x; r <= k; r += blockDim.x) cp_async16(dst + (size_t)q * n + r, src + r);
       }
       cp_async_commit();
     };
-    __syncthreads();                                        // previous round finished with both buffers
-    prefetch(0, 0);
-    for (int b = 0; b < nblk; ++b) {
-      const int buf = b & 1;
-      cp_async_wait<0>();
-      __syncthreads();                                      // block b landed; everyone left block b-1
-      if (b + 1 < nblk) prefetch(b + 1, buf ^ 1);
-      const cplx* tile = sH + (size_t)buf * INVIT_CB * n;
-      const int kb = n - 1 - b * INVIT_CB;
-      for (int q = 0; q < INVIT_CB; ++q) {
-        const int k = kb - q;
-        if (k < 1) break;
-        if (!live || k > m - 1) continue;
-        if (k == m - 1) {                                   // start: carried column = column m-1 of H - lam I
-          const cplx* hc = H + (size_t)(m - 1) * n;
+    if (live) {                                             // start: carried column = column m-1 of H - lam I
+      const cplx* hc = H + (size_t)(m - 1) * n;
 #pragma unroll
-          for (int s = 0; s < NS; ++s) {
-            const int r = 32 * s + lane;
-            if (r < m) {
-              cplx a = hc[r];
-              if (r == m - 1) a -= lm;
-              c[s] = a; y[s] = mk(eps3, 0.0);
-            }
-          }
-          cdiag = hc[m - 1] - lm;
-          ydiag = mk(eps3, 0.0);
+      for (int s = 0; s < NS; ++s) {
+        const int r = 32 * s + lane;
+        if (r < m) {
+          cplx a = hc[r];
+          if (r == m - 1) a -= lm;
+          c[s] = a; y[s] = mk(eps3, 0.0);
         }
-        const cplx* acol = tile + (size_t)q * n;            // column k-1
-        const cplx ak = acol[k];
-        const bool sw = cabs1(ak) > cabs1(cdiag);
-        cplx piv = sw ? ak : cdiag;
-        if (is_zero(piv)) piv = mk(eps3, 0.0);
-        const cplx yk = cdiv(ydiag, piv);
-        const cplx mq = cdiv(sw ? cdiag : ak, piv);
-        cplx cnext = mk(0.0, 0.0), ynext = mk(0.0, 0.0);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          if (32 * s <= k) {
-            const int r = 32 * s + lane;
-            if (r < k) {
-              cplx a = acol[r];
-              if (r == k - 1) a -= lm;
-              const cplx cr = c[s];
-              const cplx u = sw ? a : cr;
-              const cplx cn = sw ? (cr - mq * a) : (a - mq * cr);
-              const cplx yn = y[s] - yk * u;
-              c[s] = cn; y[s] = yn;
-              if (r == k - 1) { cnext = cn; ynext = yn; }
-            } else if (r == k) {
-              c[s] = mq; y[s] = yk;
-              if (sw) flags |= (1u << s);
-            }
-          }
-        }
-        cdiag = shfl_c(cnext, (k - 1) & 31);
-        ydiag = shfl_c(ynext, (k - 1) & 31);
       }
+      cdiag = hc[m - 1] - lm;
+      ydiag = mk(eps3, 0.0);
     }
+    __syncthreads();                                        // previous round finished with both buffers
+    int buf = 0;
+    prefetch((n - 1) >> 3, 0);
+    InvitSlot<NS, NS - 1>::run(n, m, live, lane, H, sH, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
     // ---- k = 0, then x = T_{m-1} ... T_1 y (forward recurrence carried by shuffles) ----
     int isbad = 0;
     if (live) {
-      if (m == 1) { cdiag = H[0] - lm; ydiag = mk(eps3, 0.0); }
       cplx piv = cdiag;
       if (is_zero(piv)) piv = mk(eps3, 0.0);
       cplx prev = cdiv(ydiag, piv);                         // current value of y[k-1]
@@ -153,9 +209,8 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
           }
         }
       }
-      // last row m-1 gets the carried value
       {
-        const int rl = m - 1;
+        const int rl = m - 1;                               // last row gets the carried value
 #pragma unroll
         for (int s = 0; s < NS; ++s)
           if (32 * s + lane == rl) y[s] = prev;

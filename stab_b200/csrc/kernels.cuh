@@ -283,7 +283,7 @@ SD_HD size_t hqr_smem_bytes(const HqrLaunch& q) {
   return b;
 }
 
-__global__ void k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q) {
+__global__ void k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q, long long* prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* sp = smem_raw;
   double* red = reinterpret_cast<double*>(sp); sp += 160 * sizeof(double);
@@ -297,6 +297,7 @@ __global__ void k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w
   sh.ctl = reinterpret_cast<SmallCtl*>(sp);
   Cta c = make_cta(red);
   const int p = blockIdx.x;
+  sh.prof = (prof && p == 0) ? prof : nullptr;
   int r = cta_hqr(c, sh, Hq + (size_t)p * hstride, n, n, ilohi[2 * p], ilohi[2 * p + 1], w + (size_t)p * n);
   if (threadIdx.x == 0) info[p] = r;
 }

@@ -19,6 +19,8 @@ bool g_inited = false;
 struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
+bool g_qrprof_on = false;
+long long* g_qrprof_dev = nullptr;
 
 #define CU(call)                                                                                   \
   do {                                                                                             \
@@ -268,9 +270,10 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
   }
   const int rounds = 4;
   int rc;
-  if (N <= 160) rc = launch_invit<5>(pl, rounds);
-  else if (N <= 320) rc = launch_invit<10>(pl, rounds);
-  else if (N <= 480) rc = launch_invit<15>(pl, rounds);
+  if (N <= 128) rc = launch_invit<4>(pl, rounds);
+  else if (N <= 256) rc = launch_invit<8>(pl, rounds);
+  else if (N <= 384) rc = launch_invit<12>(pl, rounds);
+  else if (N <= 512) rc = launch_invit<16>(pl, rounds);
   else rc = launch_invit<20>(pl, rounds);
   if (rc) return 1;
   // vectors the fast kernel rejected (no growth / overflow): ZLAEIN's retry vectors, v1 kernel, Hessenberg basis
@@ -320,7 +323,13 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
       return fail("libstabgpu: invalid QR tuning (window too small for the shift count)");
     size_t sm = hqr_smem_bytes(q);
     CU(cudaFuncSetAttribute(k_hqr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_hqr<<<np, g_tune.qr_threads, sm, s>>>(Hq, st, N, pl->ilohi.p, pl->w.p, pl->info_qr.p, q);
+    long long* prof = nullptr;
+    if (g_qrprof_on) {
+      if (!g_qrprof_dev) CU(cudaMalloc(&g_qrprof_dev, 16 * sizeof(long long)));
+      CU(cudaMemsetAsync(g_qrprof_dev, 0, 16 * sizeof(long long), s));
+      prof = g_qrprof_dev;
+    }
+    k_hqr<<<np, g_tune.qr_threads, sm, s>>>(Hq, st, N, pl->ilohi.p, pl->w.p, pl->info_qr.p, q, prof);
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(pl->ev[ST_QR + 1], s));
@@ -400,6 +409,13 @@ int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb)
   if (name && name_len > 0) { std::strncpy(name, pr.name, name_len - 1); name[name_len - 1] = 0; }
   if (sm_count) *sm_count = pr.multiProcessorCount;
   if (mem_gb) *mem_gb = (double)pr.totalGlobalMem / 1.0e9;
+  return 0;
+}
+
+/* debug: cycle counters of the QR kernel for matrix 0 of the last run (not part of the public header) */
+int stabgpu_debug_qr_profile(int enable, long long* out16) {
+  g_qrprof_on = enable != 0;
+  if (out16 && g_qrprof_dev) { cudaDeviceSynchronize(); cudaMemcpy(out16, g_qrprof_dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost); }
   return 0;
 }
 

@@ -42,7 +42,7 @@ int emu_hqr(cplx* H, int n, int ilo, int ihi, cplx* w, int W, int ns_max, int st
   std::vector<Refl> rec((size_t)steps_max * ns_max), cur(ns_max);
   SmallCtl ctl;
   sh.win = win.data(); sh.rec = rec.data(); sh.steps_max = steps_max; sh.ns_max = ns_max;
-  sh.cur = cur.data(); sh.shifts = shifts.data(); sh.sm = sm.data(); sh.ctl = &ctl;
+  sh.cur = cur.data(); sh.shifts = shifts.data(); sh.sm = sm.data(); sh.ctl = &ctl; sh.prof = nullptr;
   return cta_hqr(c, sh, H, n, n, ilo, ihi, w);
 }
 
