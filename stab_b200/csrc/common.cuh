@@ -15,11 +15,13 @@
 #define SD_HD inline
 #define SD_DEV inline
 #define SD_SHARED static
+#define SD_NOINLINE inline
 #else
 #include <cuda_runtime.h>
 #define SD_HD __host__ __device__ __forceinline__
 #define SD_DEV __device__ __forceinline__
 #define SD_SHARED __shared__
+#define SD_NOINLINE __device__ __noinline__
 #endif
 
 namespace stab {

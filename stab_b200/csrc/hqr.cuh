@@ -31,19 +31,25 @@ SD_DEV void grp_sync(const Grp& g) {
 #endif
 }
 
-// 2-element ZLARFG: on return x1 := beta (real), returns {v2, tau}
+// 2-element ZLARFG: on return x1 := beta (real), returns {v2, tau}.
+// FP64 divide / sqrt cost ~260 dependent cycles each on sm_100, and this sits on the critical path
+// of every bulge step: one sqrt and two independent reciprocals (no Smith division; the operands
+// are scaled by a power of two only when their squares could leave the safe range).
 SD_DEV Refl larfg2(cplx& x1, cplx x2) {
   Refl r; r.v2 = mk(0.0, 0.0); r.tau = mk(0.0, 0.0);
-  double xn2 = abs2(x2);
-  if (xn2 == 0.0 && x1.im == 0.0) return r;
-  // scale to avoid spurious over/underflow in the squares
-  double sc = fmax(cabs1(x1), cabs1(x2));
-  cplx a = mk(x1.re / sc, x1.im / sc), b = mk(x2.re / sc, x2.im / sc);
-  double nrm = sqrt(abs2(a) + abs2(b));
-  double beta = -copysign(nrm, a.re);
-  r.tau = mk((beta - a.re) / beta, -a.im / beta);
-  r.v2 = cdiv(b, mk(a.re - beta, a.im));
-  x1 = mk(beta * sc, 0.0);
+  if (is_zero(x2) && x1.im == 0.0) return r;
+  const double mx = fmax(cabs1(x1), cabs1(x2));
+  double sc = 1.0;
+  if (mx > 1.0e140 || mx < 1.0e-140) sc = ldexp(1.0, -ilogb(mx));
+  const cplx a = mk(x1.re * sc, x1.im * sc), b = mk(x2.re * sc, x2.im * sc);
+  const double nrm = sqrt(fma(a.re, a.re, fma(a.im, a.im, fma(b.re, b.re, b.im * b.im))));
+  const double beta = -copysign(nrm, a.re);
+  const double ib = 1.0 / beta;
+  r.tau = mk((beta - a.re) * ib, -a.im * ib);
+  const cplx d = mk(a.re - beta, a.im);                 // |d| >= |beta| > 0: no cancellation by the sign choice
+  const double id = 1.0 / fma(d.re, d.re, d.im * d.im);
+  r.v2 = mk((b.re * d.re + b.im * d.im) * id, (b.im * d.re - b.re * d.im) * id);
+  x1 = mk(beta / sc, 0.0);
   return r;
 }
 
@@ -91,32 +97,38 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
       if (rec) rec[(t - ta) * ns + b] = r;
     }
     grp_sync(g);
+    // left / right applications: one thread per (column | row, bulge group); the bulges of one
+    // time step touch disjoint row / column pairs, so a thread's updates are independent
     const int ncol = chi + 1;
-    for (int q = g.tid; q < ns * ncol; q += g.nt) {
-      const int b = q / ncol, col = q - b * ncol;
-      const int s = t - 2 * b;
-      if (s < 0 || s > smax) continue;
-      const int kl = L + s - g0;
-      if (col < kl) continue;
-      const Refl r = cur[b];
-      if (is_zero(r.tau)) continue;
-      cplx x1 = S[kl + col * lds], x2 = S[kl + 1 + col * lds];
-      apply_left(r, x1, x2);
-      S[kl + col * lds] = x1; S[kl + 1 + col * lds] = x2;
+    int ngrp = g.nt / ncol; if (ngrp < 1) ngrp = 1; if (ngrp > ns) ngrp = ns;
+    for (int idx = g.tid; idx < ncol * ngrp; idx += g.nt) {
+      const int col = idx % ncol, grp = idx / ncol;
+      for (int b = grp; b < ns; b += ngrp) {
+        const int s = t - 2 * b;
+        if (s < 0 || s > smax) continue;
+        const int kl = L + s - g0;
+        if (col < kl) continue;
+        const Refl r = cur[b];
+        cplx x1 = S[kl + col * lds], x2 = S[kl + 1 + col * lds];
+        apply_left(r, x1, x2);
+        S[kl + col * lds] = x1; S[kl + 1 + col * lds] = x2;
+      }
     }
     grp_sync(g);
-    for (int q = g.tid; q < ns * ncol; q += g.nt) {
-      const int b = q / ncol, row = q - b * ncol;
-      const int s = t - 2 * b;
-      if (s < 0 || s > smax) continue;
-      const int kl = L + s - g0;
-      int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
-      if (row < rlo || row > rmax) continue;
-      const Refl r = cur[b];
-      if (is_zero(r.tau)) continue;
-      cplx x1 = S[row + kl * lds], x2 = S[row + (kl + 1) * lds];
-      apply_right(r, x1, x2);
-      S[row + kl * lds] = x1; S[row + (kl + 1) * lds] = x2;
+    for (int idx = g.tid; idx < ncol * ngrp; idx += g.nt) {
+      const int row = idx % ncol, grp = idx / ncol;
+      if (row < rlo) continue;
+      for (int b = grp; b < ns; b += ngrp) {
+        const int s = t - 2 * b;
+        if (s < 0 || s > smax) continue;
+        const int kl = L + s - g0;
+        int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
+        if (row > rmax) continue;
+        const Refl r = cur[b];
+        cplx x1 = S[row + kl * lds], x2 = S[row + (kl + 1) * lds];
+        apply_right(r, x1, x2);
+        S[row + kl * lds] = x1; S[row + (kl + 1) * lds] = x2;
+      }
     }
     grp_sync(g);
   }
@@ -239,6 +251,92 @@ struct HqrSmem {
 #define HQR_COUNT(i) do { if (sh.prof && c.tid == 0) sh.prof[i] += 1; } while (0)
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// Off-window (slab) update of ONE line -- a column of the left slab (positions = rows, stride 1)
+// or a row of the right slab (positions = columns, stride ldh) -- with the reflectors recorded
+// for the time steps [ta, tb) of a chain of NSB bulges, as a register-resident systolic pipeline:
+// bulge b is a stage that holds one element (st[b]), consumes the element its predecessor
+// emitted one time step earlier (pipe[b]; stage 0 reads memory), applies reflector (t, b) to the
+// pair, emits the upper element to stage b+1 (the last stage writes memory) and keeps the lower
+// one.  Every element of the line is loaded once and stored once per pass; all 2*NSB in-flight
+// elements live in registers (static indexing: the stage loop is unrolled).  Stage b at time t
+// acts on positions (L+s, L+s+1), s = t-2b, for 0 <= s <= smax; s = -1 is its start-up
+// (absorb the first element), s = smax+1 its flush.  STEADY: every stage is active at every
+// step of the pass (no start-up / flush inside), so the mode tests vanish.
+// ---------------------------------------------------------------------------------------------
+constexpr int SLAB_PF = 4;   // input prefetch distance (time steps)
+
+template <int NSB, bool RIGHT, bool STEADY>
+SD_NOINLINE void slab_line(cplx* base, size_t stride, int L, int smax, int ta, int tb, const Refl* rec) {
+  cplx st[NSB], pipe[NSB];
+#pragma unroll
+  for (int b = 0; b < NSB; ++b) {                         // prologue: elements in flight at time ta
+    const int s = ta - 2 * b;
+    st[b] = mk(0.0, 0.0); pipe[b] = mk(0.0, 0.0);
+    if (STEADY || (s >= 0 && s <= smax + 1)) st[b] = base[(size_t)(L + s) * stride];
+    if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) pipe[b] = base[(size_t)(L + s + 1) * stride];
+  }
+  cplx inq[SLAB_PF];                                      // stage 0's input: position L+t+1 at time t
+#pragma unroll
+  for (int u = 0; u < SLAB_PF; ++u) {
+    const int t = ta + u;
+    inq[u] = (t < tb && t <= smax) ? base[(size_t)(L + t + 1) * stride] : mk(0.0, 0.0);
+  }
+  for (int t0 = ta; t0 < tb; t0 += SLAB_PF) {
+#pragma unroll
+    for (int u = 0; u < SLAB_PF; ++u) {
+      const int t = t0 + u;
+      if (t < tb) {
+        const cplx xin = inq[u];
+        {
+          const int tn = t + SLAB_PF;
+          if (tn < tb && tn <= smax) inq[u] = base[(size_t)(L + tn + 1) * stride];
+        }
+        const Refl* rt = rec + (size_t)(t - ta) * NSB;
+#pragma unroll
+        for (int bb = 0; bb < NSB; ++bb) {
+          const int b = NSB - 1 - bb;                     // descending: consume pipe[b] before stage b-1 refills it
+          const int s = t - 2 * b;
+          if (STEADY || (s >= 0 && s <= smax)) {
+            cplx x1 = st[b];
+            cplx x2 = (b == 0) ? xin : pipe[b];
+            const Refl r = rt[b];
+            if (RIGHT) apply_right(r, x1, x2); else apply_left(r, x1, x2);   // tau = 0 is an exact identity
+            if (b == NSB - 1) base[(size_t)(L + s) * stride] = x1; else pipe[b + 1 < NSB ? b + 1 : b] = x1;
+            st[b] = x2;
+          } else if (s == -1) {
+            if (b >= 1) st[b] = pipe[b];
+          } else if (s == smax + 1) {
+            if (b == NSB - 1) base[(size_t)(L + s) * stride] = st[b]; else pipe[b + 1 < NSB ? b + 1 : b] = st[b];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NSB; ++b) {                         // epilogue: park the elements still in flight
+    const int s = tb - 2 * b;
+    if (STEADY || (s >= 0 && s <= smax + 1)) base[(size_t)(L + s) * stride] = st[b];
+    if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) base[(size_t)(L + s + 1) * stride] = pipe[b];
+  }
+}
+
+template <int NSB>
+SD_DEV void slabs_stream(const Cta& c, cplx* H, int ldh, int L, int I, int g0, int g1, int ta, int tb, const Refl* rec) {
+  const int smax = I - 1 - L;
+  const bool steady = (ta >= 2 * (NSB - 1)) && (tb - 1 <= smax);
+  // left slab: rows of the window, columns (g1, I]; one thread per column
+  for (int col = g1 + 1 + c.tid; col <= I; col += c.nt) {
+    if (steady) slab_line<NSB, false, true>(H + (size_t)col * ldh, 1, L, smax, ta, tb, rec);
+    else slab_line<NSB, false, false>(H + (size_t)col * ldh, 1, L, smax, ta, tb, rec);
+  }
+  // right slab: rows [L, g0), columns of the chain; one thread per row
+  for (int row = L + c.tid; row < g0; row += c.nt) {
+    if (steady) slab_line<NSB, true, true>(H + row, (size_t)ldh, L, smax, ta, tb, rec);
+    else slab_line<NSB, true, false>(H + row, (size_t)ldh, L, smax, ta, tb, rec);
+  }
+}
+
 // One multishift sweep over the active block [L, I] of the global Hessenberg matrix H.
 SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, int L, int I, int ns) {
   Grp g; g.tid = c.tid; g.nt = c.nt; g.warp = false;
@@ -275,6 +373,14 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
     }
     HQR_PROF(2);
     const int smax = I - 1 - L;
+    if (ns == 16) {
+      cta_sync();                                   // window stores precede slab reads of neighbouring entries? (disjoint) -- rec is final
+      slabs_stream<16>(c, H, ldh, L, I, g0, g1, ta, tb, sh.rec);
+      cta_sync();
+      HQR_PROF(4);
+      ta = tb;
+      continue;
+    }
     // left slab: rows [g0, g1], columns (g1, I]; thread per column, bulge-major with carry
     for (int col = g1 + 1 + c.tid; col <= I; col += c.nt) {
       cplx* hc = H + (size_t)col * ldh;
@@ -361,7 +467,18 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
         sh.win[row + col * sh.ldw] = (row <= col + 1) ? H[(L + row) + (size_t)(L + col) * ldh] : mk(0.0, 0.0);
       }
       cta_sync();
-      int bad = smem_hqr(g, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur);
+      int bad = 0;
+      if (m <= 40) {                           // small: one warp with warp-level barriers beats CTA barriers
+        if (c.wid == 0) {
+          Grp gw; gw.tid = c.lane; gw.nt = c.ws; gw.warp = true;
+          bad = smem_hqr(gw, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur);
+          if (c.lane == 0) sh.ctl->pad = bad;
+        }
+        cta_sync();
+        bad = sh.ctl->pad;
+      } else {
+        bad = smem_hqr(g, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur);
+      }
       if (bad) info += bad;
       I = L - 1; stagn = 0;
       cta_sync();
@@ -389,7 +506,10 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
         sh.sm[row + col * lds] = (row <= col + 1) ? H[(k0 + row) + (size_t)(k0 + col) * ldh] : mk(0.0, 0.0);
       }
       cta_sync();
-      smem_hqr(g, sh.sm, lds, ns, sh.shifts, sh.ctl, sh.cur);
+      if (c.wid == 0) {                        // a 16x16 problem: one warp, warp-level barriers
+        Grp gw; gw.tid = c.lane; gw.nt = c.ws; gw.warp = true;
+        smem_hqr(gw, sh.sm, lds, ns, sh.shifts, sh.ctl, sh.cur);
+      }
       cta_sync();
     }
     HQR_PROF(1);
