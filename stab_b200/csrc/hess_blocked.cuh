@@ -32,6 +32,7 @@ struct HessBatch {
   cplx* Ypart;          // n x CHUNKS per matrix
   cplx* W;              // NB x n per matrix
   int P;
+  int mat0;             // first matrix of this launch group (the batch is split over two streams)
 };
 
 SD_DEV cplx hb_v(const cplx* A, int lda, int k, int ihi, int r, int l) {   // V(r, l) of the panel starting at k

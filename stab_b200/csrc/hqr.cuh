@@ -42,28 +42,40 @@ SD_DEV Refl larfg2(cplx& x1, cplx x2) {
   double sc = 1.0;
   if (mx > 1.0e140 || mx < 1.0e-140) sc = ldexp(1.0, -ilogb(mx));
   const cplx a = mk(x1.re * sc, x1.im * sc), b = mk(x2.re * sc, x2.im * sc);
-  const double nrm = sqrt(fma(a.re, a.re, fma(a.im, a.im, fma(b.re, b.re, b.im * b.im))));
-  const double beta = -copysign(nrm, a.re);
-  const double ib = 1.0 / beta;
+  const double ss = fma(a.re, a.re, fma(a.im, a.im, fma(b.re, b.re, b.im * b.im)));
+#ifdef STAB_EMU
+  const double inrm = 1.0 / sqrt(ss);
+#else
+  const double inrm = rsqrt(ss);                          // one MUFU + Newton: no divide, no sqrt on the critical path
+#endif
+  const double nrm = ss * inrm;
+  const double sg = (a.re >= 0.0) ? 1.0 : -1.0;           // copysign(1, a.re) with +0 -> +
+  const double beta = -sg * nrm;
+  const double ib = -sg * inrm;                           // 1 / beta
   r.tau = mk((beta - a.re) * ib, -a.im * ib);
   const cplx d = mk(a.re - beta, a.im);                 // |d| >= |beta| > 0: no cancellation by the sign choice
+#ifdef STAB_EMU
   const double id = 1.0 / fma(d.re, d.re, d.im * d.im);
+#else
+  const double id = __drcp_rn(fma(d.re, d.re, d.im * d.im));
+#endif
   r.v2 = mk((b.re * d.re + b.im * d.im) * id, (b.im * d.re - b.re * d.im) * id);
   x1 = mk(beta / sc, 0.0);
   return r;
 }
 
-SD_DEV void apply_left(const Refl& r, cplx& x1, cplx& x2) {    // [x1;x2] := (I - conj(tau) v v^H) [x1;x2]
+SD_DEV void apply_left(const Refl& r, cplx& x1, cplx& x2) {    // [x1;x2] := (I - conj(tau) v v^H) [x1;x2]   (14 FMA-class ops)
   cplx s = x1; fma_acc_conj(s, r.v2, x2);
-  s = conj(r.tau) * s;
-  x1 -= s;
-  x2 -= s * r.v2;
+  const cplx t = mk(fma(r.tau.re, s.re, r.tau.im * s.im), fma(r.tau.re, s.im, -(r.tau.im * s.re)));   // conj(tau) * s
+  x1.re -= t.re; x1.im -= t.im;
+  fms_acc(x2, t, r.v2);
 }
 SD_DEV void apply_right(const Refl& r, cplx& x1, cplx& x2) {   // [x1 x2] := [x1 x2] (I - tau v v^H)
   cplx s = x1; fma_acc(s, x2, r.v2);
-  s = s * r.tau;
-  x1 -= s;
-  x2 -= mulc(s, r.v2);
+  const cplx t = mk(fma(s.re, r.tau.re, -(s.im * r.tau.im)), fma(s.re, r.tau.im, s.im * r.tau.re));   // s * tau
+  x1.re -= t.re; x1.im -= t.im;
+  x2.re = fma(-t.re, r.v2.re, x2.re); x2.re = fma(-t.im, r.v2.im, x2.re);                            // x2 -= t * conj(v2)
+  x2.im = fma(-t.im, r.v2.re, x2.im); x2.im = fma(t.re, r.v2.im, x2.im);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -73,8 +85,14 @@ SD_DEV void apply_right(const Refl& r, cplx& x1, cplx& x2) {   // [x1 x2] := [x1
 // rows >= rlo.  `rec` (optional) receives the reflectors, (t-ta)*ns + b.
 // ---------------------------------------------------------------------------------------------
 SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int L, int I,
-                  const cplx* shifts, int ns, int ta, int tb, Refl* rec, Refl* cur) {
+                  const cplx* shifts, int ns, int ta, int tb, Refl* rec, Refl* cur, long long* prof = nullptr) {
   const int smax = I - 1 - L;
+#ifndef STAB_EMU
+  long long pc0 = (prof && g.tid == 0) ? clock64() : 0;
+#define CHASE_PROF(i) do { if (prof && g.tid == 0) { long long t1_ = clock64(); prof[i] += t1_ - pc0; pc0 = t1_; } } while (0)
+#else
+#define CHASE_PROF(i)
+#endif
   for (int t = ta; t < tb; ++t) {
     for (int b = g.tid; b < ns; b += g.nt) {
       const int s = t - 2 * b;
@@ -97,40 +115,88 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
       if (rec) rec[(t - ta) * ns + b] = r;
     }
     grp_sync(g);
+    CHASE_PROF(10);
     // left / right applications: one thread per (column | row, bulge group); the bulges of one
-    // time step touch disjoint row / column pairs, so a thread's updates are independent
+    // time step touch disjoint row / column pairs, so a thread's updates are independent: load all
+    // operands, then all the arithmetic, then all the stores (ILP instead of one latency chain per bulge)
     const int ncol = chi + 1;
-    int ngrp = g.nt / ncol; if (ngrp < 1) ngrp = 1; if (ngrp > ns) ngrp = ns;
-    for (int idx = g.tid; idx < ncol * ngrp; idx += g.nt) {
-      const int col = idx % ncol, grp = idx / ncol;
-      for (int b = grp; b < ns; b += ngrp) {
-        const int s = t - 2 * b;
-        if (s < 0 || s > smax) continue;
-        const int kl = L + s - g0;
-        if (col < kl) continue;
-        const Refl r = cur[b];
-        cplx x1 = S[kl + col * lds], x2 = S[kl + 1 + col * lds];
-        apply_left(r, x1, x2);
-        S[kl + col * lds] = x1; S[kl + 1 + col * lds] = x2;
+    constexpr int NPT = 8;                                  // bulges per thread
+    const int ngrp = (ns + NPT - 1) / NPT;
+    if (ncol * ngrp <= g.nt) {
+      const int col = g.tid % ncol, grp = g.tid / ncol;     // also the row index in the right phase
+      const bool mine = g.tid < ncol * ngrp;
+      cplx x1[NPT], x2[NPT]; Refl rf[NPT]; int kk[NPT];
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) {
+        const int b = grp + u * ngrp, s = t - 2 * b;
+        kk[u] = -1;
+        rf[u].tau = mk(0.0, 0.0); rf[u].v2 = mk(0.0, 0.0); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
+        if (mine && b < ns && s >= 0 && s <= smax) {
+          const int kl = L + s - g0;
+          if (col >= kl) { kk[u] = kl; rf[u] = cur[b]; x1[u] = S[kl + col * lds]; x2[u] = S[kl + 1 + col * lds]; }
+        }
       }
-    }
-    grp_sync(g);
-    for (int idx = g.tid; idx < ncol * ngrp; idx += g.nt) {
-      const int row = idx % ncol, grp = idx / ncol;
-      if (row < rlo) continue;
-      for (int b = grp; b < ns; b += ngrp) {
-        const int s = t - 2 * b;
-        if (s < 0 || s > smax) continue;
-        const int kl = L + s - g0;
-        int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
-        if (row > rmax) continue;
-        const Refl r = cur[b];
-        cplx x1 = S[row + kl * lds], x2 = S[row + (kl + 1) * lds];
-        apply_right(r, x1, x2);
-        S[row + kl * lds] = x1; S[row + (kl + 1) * lds] = x2;
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) apply_left(rf[u], x1[u], x2[u]);
+#pragma unroll
+      for (int u = 0; u < NPT; ++u)
+        if (kk[u] >= 0) { S[kk[u] + col * lds] = x1[u]; S[kk[u] + 1 + col * lds] = x2[u]; }
+      grp_sync(g);
+      CHASE_PROF(11);
+      const int row = col;
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) {
+        const int b = grp + u * ngrp, s = t - 2 * b;
+        kk[u] = -1;
+        rf[u].tau = mk(0.0, 0.0); rf[u].v2 = mk(0.0, 0.0); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
+        if (mine && row >= rlo && b < ns && s >= 0 && s <= smax) {
+          const int kl = L + s - g0;
+          int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
+          if (row <= rmax) { kk[u] = kl; rf[u] = cur[b]; x1[u] = S[row + kl * lds]; x2[u] = S[row + (kl + 1) * lds]; }
+        }
       }
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) apply_right(rf[u], x1[u], x2[u]);
+#pragma unroll
+      for (int u = 0; u < NPT; ++u)
+        if (kk[u] >= 0) { S[row + kk[u] * lds] = x1[u]; S[row + (kk[u] + 1) * lds] = x2[u]; }
+      grp_sync(g);
+    } else {
+      // generic path (small thread groups / many bulges per thread)
+      int ng = g.nt / ncol; if (ng < 1) ng = 1; if (ng > ns) ng = ns;
+      for (int idx = g.tid; idx < ncol * ng; idx += g.nt) {
+        const int col = idx % ncol, grp = idx / ncol;
+        for (int b = grp; b < ns; b += ng) {
+          const int s = t - 2 * b;
+          if (s < 0 || s > smax) continue;
+          const int kl = L + s - g0;
+          if (col < kl) continue;
+          const Refl r = cur[b];
+          cplx x1 = S[kl + col * lds], x2 = S[kl + 1 + col * lds];
+          apply_left(r, x1, x2);
+          S[kl + col * lds] = x1; S[kl + 1 + col * lds] = x2;
+        }
+      }
+      grp_sync(g);
+      CHASE_PROF(11);
+      for (int idx = g.tid; idx < ncol * ng; idx += g.nt) {
+        const int row = idx % ncol, grp = idx / ncol;
+        if (row < rlo) continue;
+        for (int b = grp; b < ns; b += ng) {
+          const int s = t - 2 * b;
+          if (s < 0 || s > smax) continue;
+          const int kl = L + s - g0;
+          int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
+          if (row > rmax) continue;
+          const Refl r = cur[b];
+          cplx x1 = S[row + kl * lds], x2 = S[row + (kl + 1) * lds];
+          apply_right(r, x1, x2);
+          S[row + kl * lds] = x1; S[row + (kl + 1) * lds] = x2;
+        }
+      }
+      grp_sync(g);
     }
-    grp_sync(g);
+    CHASE_PROF(12);
   }
 }
 
@@ -238,7 +304,7 @@ struct HqrSmem {
   cplx* shifts;  // ns_max
   cplx* sm;      // ns_max * (ns_max + 1)   trailing block for the shift computation
   SmallCtl* ctl;
-  long long* prof;   // optional cycle counters (debug): scan, shifts, window io, chase, left slab, right slab, small blocks, #sweeps, #passes
+  long long* prof;   // optional cycle counters (debug), in SHARED memory (copied out by the kernel at the end): scan, shifts, window io, chase, left slab, right slab, small blocks, #sweeps, #passes
 };
 
 #if defined(STAB_EMU)
@@ -365,7 +431,7 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
     }
     cta_sync();
     HQR_PROF(2);
-    chase(g, sh.win, ldw, g0, 0, wsz - 1, L, I, sh.shifts, ns, ta, tb, sh.rec, sh.cur);
+    chase(g, sh.win, ldw, g0, 0, wsz - 1, L, I, sh.shifts, ns, ta, tb, sh.rec, sh.cur, sh.prof);
     HQR_PROF(3);
     for (int q = c.tid; q < wsz * wsz; q += c.nt) {
       const int col = q / wsz, row = q - col * wsz;

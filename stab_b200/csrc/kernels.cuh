@@ -205,30 +205,30 @@ __global__ void __launch_bounds__(256) k_hb_panel_step(HessBatch hb, int panel, 
   cplx* sw = sb + hb.n;
   cplx* st = sw + HB_NB;
   Cta c = make_cta(red);
-  cta_hb_panel_step(c, hb, blockIdx.x, panel, j, red, sb, sw, st);
+  cta_hb_panel_step(c, hb, hb.mat0 + blockIdx.x, panel, j, red, sb, sw, st);
 }
 
 __global__ void __launch_bounds__(HB_GEMV_ROWS) k_hb_gemv(HessBatch hb, int panel, int j) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta c = make_cta(nullptr);
-  cta_hb_gemv(c, hb, blockIdx.z, panel, j, blockIdx.x, blockIdx.y, reinterpret_cast<cplx*>(smem_raw));
+  cta_hb_gemv(c, hb, hb.mat0 + blockIdx.z, panel, j, blockIdx.x, blockIdx.y, reinterpret_cast<cplx*>(smem_raw));
 }
 
 template <int PHASE, bool USE_MMA>
 __global__ void __launch_bounds__(GEMM_THREADS) k_hb_gemm(HessBatch hb, int panel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta c = make_cta(nullptr);
-  cta_hb_gemm<PHASE, USE_MMA>(c, hb, blockIdx.z, panel, blockIdx.x, blockIdx.y, reinterpret_cast<double*>(smem_raw));
+  cta_hb_gemm<PHASE, USE_MMA>(c, hb, hb.mat0 + blockIdx.z, panel, blockIdx.x, blockIdx.y, reinterpret_cast<double*>(smem_raw));
 }
 
 __global__ void k_hb_ytop_T(HessBatch hb, int panel) {
   Cta c = make_cta(nullptr);
-  cta_hb_ytop_T(c, hb, blockIdx.y, panel, blockIdx.x);
+  cta_hb_ytop_T(c, hb, hb.mat0 + blockIdx.y, panel, blockIdx.x);
 }
 
 __global__ void k_hb_w_T(HessBatch hb, int panel) {
   Cta c = make_cta(nullptr);
-  const int mat = blockIdx.y, n = hb.n;
+  const int mat = hb.mat0 + blockIdx.y, n = hb.n;
   const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
   const int k = ilo + panel * HB_NB;
   if (k >= ihi) return;
@@ -297,9 +297,13 @@ __global__ void k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w
   sh.ctl = reinterpret_cast<SmallCtl*>(sp);
   Cta c = make_cta(red);
   const int p = blockIdx.x;
-  sh.prof = (prof && p == 0) ? prof : nullptr;
+  __shared__ long long sprof[16];
+  sh.prof = (prof && p == 0) ? sprof : nullptr;
+  if (sh.prof && threadIdx.x < 16) sprof[threadIdx.x] = 0;
+  __syncthreads();
   int r = cta_hqr(c, sh, Hq + (size_t)p * hstride, n, n, ilohi[2 * p], ilohi[2 * p + 1], w + (size_t)p * n);
   if (threadIdx.x == 0) info[p] = r;
+  if (sh.prof && threadIdx.x < 16) prof[threadIdx.x] = sprof[threadIdx.x];
 }
 
 // ---- stage 5: sort (stable, ascending imaginary part) --------------------------------------------
@@ -364,12 +368,12 @@ template <int PHASE, bool USE_MMA>
 __global__ void __launch_bounds__(GEMM_THREADS) k_bt_gemm(HessBatch hb, cplx* X, size_t xstride, int panel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta c = make_cta(nullptr);
-  cta_bt_gemm<PHASE, USE_MMA>(c, hb, X, xstride, blockIdx.z, panel, blockIdx.x, blockIdx.y, reinterpret_cast<double*>(smem_raw));
+  cta_bt_gemm<PHASE, USE_MMA>(c, hb, X, xstride, hb.mat0 + blockIdx.z, panel, blockIdx.x, blockIdx.y, reinterpret_cast<double*>(smem_raw));
 }
 
 __global__ void k_bt_w_T(HessBatch hb, int panel) {
   Cta c = make_cta(nullptr);
-  const int mat = blockIdx.y, n = hb.n;
+  const int mat = hb.mat0 + blockIdx.y, n = hb.n;
   const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
   if (ilo + panel * HB_NB >= ihi) return;
   cta_hb_w_T(c, hb.T + ((size_t)mat * hb.P + panel) * HB_NB * HB_NB, hb.W + (size_t)mat * n * HB_NB, n, blockIdx.x, false);

@@ -16,7 +16,7 @@ namespace {
 thread_local std::string g_err;
 int g_device = -1;
 bool g_inited = false;
-struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
+struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; int hess_streams = 1; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
 bool g_qrprof_on = false;
@@ -85,7 +85,9 @@ struct stabgpu_plan {
   int cap = 0, npts = 0;
   bool cap_limited = false;   // cap was clipped by device memory
   int want_vectors = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  std::vector<cudaEvent_t> evA, evB;
   // grid / profile
   DBuf<double> vm, g2, g22, deta, d2eta, D1, D2, Dt2w, h5;
   bool has_h5 = false;
@@ -149,26 +151,78 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
       pl->hbYp.alloc((size_t)cap * N * HB_CHUNKS) || pl->hbW.alloc((size_t)cap * N * HB_NB)) return 1;
   if (pl->ilohi.alloc(2 * (size_t)cap) || pl->info_lu.alloc(cap) || pl->info_qr.alloc(cap) || pl->info_v.alloc(cap)) return 1;
   CU(cudaStreamCreate(&pl->stream));
+  CU(cudaStreamCreate(&pl->stream2));
+  CU(cudaEventCreateWithFlags(&pl->evFork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&pl->evJoin, cudaEventDisableTiming));
+  pl->evA.resize(pl->hbP); pl->evB.resize(pl->hbP);
+  for (int i = 0; i < pl->hbP; ++i) {
+    CU(cudaEventCreateWithFlags(&pl->evA[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&pl->evB[i], cudaEventDisableTiming));
+  }
   for (int i = 0; i <= ST_N; ++i) CU(cudaEventCreate(&pl->ev[i]));
   return 0;
 }
 
 template <int PHASE>
-int launch_hb_gemm(stabgpu_plan* pl, const HessBatch& hb, int panel, int ti, int tj, size_t smem, bool mma) {
-  dim3 grid(ti, tj, pl->npts);
+int launch_hb_gemm(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, int panel, int ti, int tj, size_t smem, bool mma) {
+  dim3 grid(ti, tj, nmat);
   if (mma) {
     CU(cudaFuncSetAttribute(k_hb_gemm<PHASE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_hb_gemm<PHASE, true><<<grid, GEMM_THREADS, smem, pl->stream>>>(hb, panel);
+    k_hb_gemm<PHASE, true><<<grid, GEMM_THREADS, smem, s>>>(hb, panel);
   } else {
     CU(cudaFuncSetAttribute(k_hb_gemm<PHASE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_hb_gemm<PHASE, false><<<grid, GEMM_THREADS, smem, pl->stream>>>(hb, panel);
+    k_hb_gemm<PHASE, false><<<grid, GEMM_THREADS, smem, s>>>(hb, panel);
   }
   CU(cudaGetLastError());
   pl->launches += 1;
   return 0;
 }
 
+// one panel of the blocked reduction for the matrices [hb.mat0, hb.mat0 + nmat) on stream s;
+// phase 1: the column loop (panel steps + HBM-bound GEMVs), phase 2: the tensor-core block updates
+int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, int p, bool mma, int phase) {
+  const int N = pl->N;
+  const size_t sm_step = 160 * sizeof(double) + ((size_t)N + 2 * HB_NB) * sizeof(cplx);
+  const size_t sm_gemv = (size_t)N * sizeof(cplx);
+  const size_t sm64 = GemmCfg<64, 64>::smem_bytes, sm6432 = GemmCfg<64, 32>::smem_bytes, sm3264 = GemmCfg<32, 64>::smem_bytes;
+  const int k0 = p * HB_NB;                                  // smallest possible panel start (ilo = 0)
+  const int rows_max = N - 1 - k0;                           // rows k+1..ihi
+  if (rows_max <= 0) return 0;
+  const int trail_max = N - (k0 + HB_NB);                    // columns k+NB..n-1
+  if (phase == 1) {
+    dim3 ggemv((rows_max + HB_GEMV_ROWS - 1) / HB_GEMV_ROWS, HB_CHUNKS, nmat);
+    for (int j = 0; j < HB_NB; ++j) {
+      k_hb_panel_step<<<nmat, 256, sm_step, s>>>(hb, p, j);
+      k_hb_gemv<<<ggemv, HB_GEMV_ROWS, sm_gemv, s>>>(hb, p, j);
+    }
+    k_hb_panel_step<<<nmat, 256, sm_step, s>>>(hb, p, HB_NB);
+    CU(cudaGetLastError());
+    pl->launches += 2 * HB_NB + 1;
+    return 0;
+  }
+  const int tm = (N + 63) / 64;
+  if (launch_hb_gemm<HB_YTOP>(pl, hb, nmat, s, p, tm, 1, sm6432, mma)) return 1;
+  k_hb_ytop_T<<<dim3((N + 127) / 128, nmat), 128, 0, s>>>(hb, p);
+  pl->launches += 1;
+  if (trail_max > 0) {
+    const int tn = (trail_max + 63) / 64;
+    if (launch_hb_gemm<HB_RIGHT_TRAIL>(pl, hb, nmat, s, p, tm, tn, sm64, mma)) return 1;
+  }
+  if (launch_hb_gemm<HB_RIGHT_PANEL>(pl, hb, nmat, s, p, tm, 1, sm6432, mma)) return 1;
+  if (trail_max > 0) {
+    const int tn = (trail_max + 63) / 64;
+    if (launch_hb_gemm<HB_LEFT_W>(pl, hb, nmat, s, p, 1, tn, sm3264, mma)) return 1;
+    k_hb_w_T<<<dim3((trail_max + 127) / 128, nmat), 128, 0, s>>>(hb, p);
+    pl->launches += 1;
+    if (launch_hb_gemm<HB_LEFT_UPD>(pl, hb, nmat, s, p, (rows_max + 63) / 64, tn, sm64, mma)) return 1;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
 // Stage 3b: A <- Hessenberg form + reflectors (ZGEHRD layout), tau, and the panel factors T.
+// The batch is split in two halves that run the same kernel schedule on two streams: the
+// HBM-bound GEMV of one half overlaps the latency-bound panel step / tensor-core updates of the other.
 int run_hessenberg(stabgpu_plan* pl) {
   const int N = pl->N, np = pl->npts;
   const size_t st = (size_t)N * N;
@@ -182,41 +236,28 @@ int run_hessenberg(stabgpu_plan* pl) {
     return 0;
   }
   const bool mma = g_tune.hess_mode == 1;
-  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP};
-  const size_t sm_step = 160 * sizeof(double) + ((size_t)N + 2 * HB_NB) * sizeof(cplx);
-  const size_t sm_gemv = (size_t)N * sizeof(cplx);
-  const size_t sm64 = GemmCfg<64, 64>::smem_bytes, sm6432 = GemmCfg<64, 32>::smem_bytes, sm3264 = GemmCfg<32, 64>::smem_bytes;
+  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0};
+  const int half = (g_tune.hess_streams >= 2 && np >= 16) ? (np + 1) / 2 : np;
+  HessBatch hb2 = hb; hb2.mat0 = half;
+  if (half < np) { CU(cudaEventRecord(pl->evFork, s)); CU(cudaStreamWaitEvent(pl->stream2, pl->evFork, 0)); }
+  // software pipeline over the two halves: the GEMV phases (memory bound) of A and B never overlap each
+  // other, each overlaps the tensor-core phase of the other half
+  const bool two = half < np;
   for (int p = 0; p < pl->hbP; ++p) {
-    const int k0 = p * HB_NB;                                  // smallest possible panel start (ilo = 0)
-    const int rows_max = N - 1 - k0;                           // rows k+1..ihi
-    if (rows_max <= 0) break;
-    const int trail_max = N - (k0 + HB_NB);                    // columns k+NB..n-1
-    dim3 ggemv((rows_max + HB_GEMV_ROWS - 1) / HB_GEMV_ROWS, HB_CHUNKS, np);
-    for (int j = 0; j < HB_NB; ++j) {
-      k_hb_panel_step<<<np, 256, sm_step, s>>>(hb, p, j);
-      k_hb_gemv<<<ggemv, HB_GEMV_ROWS, sm_gemv, s>>>(hb, p, j);
+    if (two && p > 0) CU(cudaStreamWaitEvent(s, pl->evB[p - 1], 0));
+    if (hess_panel(pl, hb, half, s, p, mma, 1)) return 1;
+    if (two) {
+      CU(cudaEventRecord(pl->evA[p], s));
+      CU(cudaStreamWaitEvent(pl->stream2, pl->evA[p], 0));
     }
-    k_hb_panel_step<<<np, 256, sm_step, s>>>(hb, p, HB_NB);
-    CU(cudaGetLastError());
-    pl->launches += 2 * HB_NB + 1;
-    const int tm = (N + 63) / 64;
-    if (launch_hb_gemm<HB_YTOP>(pl, hb, p, tm, 1, sm6432, mma)) return 1;
-    k_hb_ytop_T<<<dim3((N + 127) / 128, np), 128, 0, s>>>(hb, p);
-    pl->launches += 1;
-    if (trail_max > 0) {
-      const int tn = (trail_max + 63) / 64;
-      if (launch_hb_gemm<HB_RIGHT_TRAIL>(pl, hb, p, tm, tn, sm64, mma)) return 1;
+    if (hess_panel(pl, hb, half, s, p, mma, 2)) return 1;
+    if (two) {
+      if (hess_panel(pl, hb2, np - half, pl->stream2, p, mma, 1)) return 1;
+      CU(cudaEventRecord(pl->evB[p], pl->stream2));
+      if (hess_panel(pl, hb2, np - half, pl->stream2, p, mma, 2)) return 1;
     }
-    if (launch_hb_gemm<HB_RIGHT_PANEL>(pl, hb, p, tm, 1, sm6432, mma)) return 1;
-    if (trail_max > 0) {
-      const int tn = (trail_max + 63) / 64;
-      if (launch_hb_gemm<HB_LEFT_W>(pl, hb, p, 1, tn, sm3264, mma)) return 1;
-      k_hb_w_T<<<dim3((trail_max + 127) / 128, np), 128, 0, s>>>(hb, p);
-      pl->launches += 1;
-      if (launch_hb_gemm<HB_LEFT_UPD>(pl, hb, p, (rows_max + 63) / 64, tn, sm64, mma)) return 1;
-    }
-    CU(cudaGetLastError());
   }
+  if (half < np) { CU(cudaEventRecord(pl->evJoin, pl->stream2)); CU(cudaStreamWaitEvent(s, pl->evJoin, 0)); }
   return 0;
 }
 
@@ -281,7 +322,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
                                               0, pl->V.p, st, pl->info_v.p, pl->vbad.p, 1);
   CU(cudaGetLastError());
   pl->launches += 1;
-  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP};
+  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0};
   const int tn = (N + 63) / 64;
   for (int p = pl->hbP - 1; p >= 0; --p) {
     const int rows_max = N - 1 - p * HB_NB;
@@ -534,6 +575,11 @@ int stabgpu_plan_destroy(stabgpu_plan* pl) {
   if (!pl) return 0;
   if (pl == g_cached) g_cached = nullptr;
   if (pl->stream) cudaStreamDestroy(pl->stream);
+  if (pl->stream2) cudaStreamDestroy(pl->stream2);
+  if (pl->evFork) cudaEventDestroy(pl->evFork);
+  if (pl->evJoin) cudaEventDestroy(pl->evJoin);
+  for (auto e : pl->evA) cudaEventDestroy(e);
+  for (auto e : pl->evB) cudaEventDestroy(e);
   for (int i = 0; i <= ST_N; ++i) if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
   delete pl;
   return 0;

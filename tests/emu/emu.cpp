@@ -186,7 +186,7 @@ extern "C" int emu_hess_blocked(cplx* A, int n, int ilo, int ihi, cplx* tau, cpl
   std::vector<cplx> sb(n), sw(HB_NB), st(HB_NB), sv(n);
   std::vector<double> smem(GemmCfg<64, 64>::smem_bytes / sizeof(double));
   int ilohi[2] = {ilo, ihi};
-  HessBatch hb{A, (size_t)n * n, n, ilohi, tau, Y.data(), T.data(), Yp.data(), W.data(), P};
+  HessBatch hb{A, (size_t)n * n, n, ilohi, tau, Y.data(), T.data(), Yp.data(), W.data(), P, 0};
   const int tiles = (n + 63) / 64;
   for (int p = 0; p < P; ++p) {
     for (int j = 0; j < HB_NB; ++j) {
