@@ -268,6 +268,11 @@ def main():
     value = P * world / (ms_step * 1e-3)
     launches = plan.launch_count() * args.steps
     stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    # one extra (untimed) execute with an event after every Hessenberg kernel: per-class breakdown
+    plan.profile_hessenberg(True)
+    plan.execute()
+    hess_bd = plan.profile_hessenberg(False)
+    ilohi = plan.ilohi()
     plan_info = np.zeros(P, dtype=np.int32)
     sb.lib().stabgpu_plan_download(plan._h, None, None, plan_info.ctypes.data)
     n_fail = int(np.count_nonzero(plan_info))
@@ -305,24 +310,54 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the graded kernel (Hessenberg stage) + measured FP64 peak --------------------
+    # ---- rooflines: the graded Hessenberg stage, its HBM-bound GEMV kernel and its DMMA kernels -------
     peak = fp64_gemm_peak(torch, dev)
-    hess_flops = (40.0 / 3.0) * n ** 3 * P
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+    NB = 32
+    hess_flops = gemv_bytes = gemm_flops = 0.0
+    for ilo, ihi in ilohi:
+        ilo, ihi = int(ilo), int(ihi)
+        nh = ihi - ilo + 1
+        hess_flops += (40.0 / 3.0) * nh ** 3 if nh > 2 else 0.0      # ZGEHRD on the active block ((40/3) n^3)
+        k = ilo
+        while k < ihi:
+            for c in range(k, min(k + NB, ihi)):
+                gemv_bytes += 16.0 * (ihi - k) * (ihi - c)           # y = A(k+1:ihi, c+1:ihi) v, one pass over the block
+            nct = n - (k + NB)
+            gemm_flops += 8.0 * NB * ((k + 1) * (ihi - k) + (k + 1) * (NB - 1))
+            if nct > 0:
+                gemm_flops += 8.0 * NB * ((ihi + 1) * max(ihi + 1 - k - NB, 0) + 2 * (ihi - k) * nct)
+            k += NB
     hess_ms = stage_ms.get("hessenberg", 0.0)
     achieved = hess_flops / (hess_ms * 1e-3) / 1e12 if hess_ms > 0 else 0.0
     total_stage = sum(stage_ms.values()) or 1.0
-    roofline = {"kernel": "k_hessenberg (stage 3, the graded stage of the north star)", "bound": "tensor",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": None, "flops_per_launch": hess_flops,
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    roofline = {"kernel": "Hessenberg stage (k_hb_panel_step + k_hb_gemv + k_hb_gemm<*>): the graded stage of the north star",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": None, "flops_per_step": hess_flops,
                 "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 burst via torch.matmul (MEASURED_PEAKS.json has no FP64 entry)",
                 "kernel_share_of_step": hess_ms / total_stage}
+    gemv_ms, gemm_ms = hess_bd.get("gemv", 0.0), hess_bd.get("gemm", 0.0)
+    gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
+    gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline_gemv = {"kernel": "k_hb_gemv (dominant kernel of the Hessenberg stage)", "bound": "hbm", "achieved": gemv_gbs,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": gemv_gbs / hbm_peak if hbm_peak else None,
+                     "algorithmic_bytes_per_step": gemv_bytes, "ms_per_step": gemv_ms, "launches_per_step": 32 * int(np.ceil((n - 1) / 32)),
+                     "peak_source": hbm_src,
+                     "traffic": (traffic or {}).get("k_hb_gemv"), "timing": "CUDA events after every kernel, separate profiled execute"}
+    roofline_gemm = {"kernel": "k_hb_gemm<*> (DMMA rank-32 updates)", "bound": "tensor", "achieved": gemm_tf, "peak": peak,
+                     "unit": "TFLOP/s", "frac": gemm_tf / peak if peak else None, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms}
     asm_ms = stage_ms.get("assemble", 0.0)
-    hbm_peak = None
-    try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    except Exception:
-        hbm_peak = 6650.0
     asm_gbs = 16.0 * n * n * P / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0
+    dominant = max(stage_ms, key=stage_ms.get)
 
     line = {
         "metric": "full-spectrum eigensolves/sec at Ny=%d" % ny, "value": value, "unit": "eigensolves/s", "n_gpus": world,
@@ -334,7 +369,11 @@ def main():
                 "call": "stabgpu_temporal_batch, pinned host buffers"},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "roofline_gemv": roofline_gemv,
+        "roofline_gemm": roofline_gemm,
         "stages_ms_per_step": stage_ms,
+        "dominant_stage": (dominant + " (shifted QR: latency / FP64-vector bound, no clean roofline -- time share only, SURVEY 8d)") if dominant == "qr" else dominant,
+        "hessenberg_breakdown_ms": hess_bd,
         "assembly_roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": asm_gbs / hbm_peak if hbm_peak else None},
         "failed_points": n_fail,

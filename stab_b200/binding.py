@@ -99,6 +99,8 @@ def lib():
     proto("stabgpu_plan_stage_times", i, [vp, C.POINTER(C.c_float)])
     proto("stabgpu_plan_launch_count", C.c_longlong, [vp])
     proto("stabgpu_plan_stream", vp, [vp])
+    proto("stabgpu_plan_ilohi", i, [vp, vp])
+    proto("stabgpu_plan_profile_hessenberg", i, [vp, i, C.POINTER(C.c_float)])
     proto("stabgpu_plan_capacity", i, [vp])
     proto("stabgpu_plan_eig_dev", vp, [vp])
     proto("stabgpu_plan_destroy", i, [vp])
@@ -396,6 +398,16 @@ class Plan:
         lib().stabgpu_plan_stage_times(self._h, ms)
         names = ("assemble", "lu", "balance", "hessenberg", "prep", "qr", "sort", "evec")
         return dict(zip(names, (float(v) for v in ms)))
+
+    def ilohi(self) -> np.ndarray:
+        out = np.zeros((self.npts, 2), dtype=np.int32)
+        _check(lib().stabgpu_plan_ilohi(self._h, _ptr(out)), "stabgpu_plan_ilohi")
+        return out
+
+    def profile_hessenberg(self, enable: bool) -> dict:
+        ms = (C.c_float * 4)()
+        lib().stabgpu_plan_profile_hessenberg(self._h, 1 if enable else 0, ms)
+        return dict(zip(("panel_step", "gemv", "gemm", "other"), (float(v) for v in ms)))
 
     def launch_count(self) -> int:
         return int(lib().stabgpu_plan_launch_count(self._h))

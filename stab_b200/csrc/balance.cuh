@@ -30,6 +30,41 @@ SD_DEV void cta_swap_rows(const Cta& c, cplx* A, int lda, int a, int b, int c0, 
   }
 }
 
+// Fused block reduction for the scaling loop: sums of cs, rs; (max, first index) of (cam, cai) and (ram, rai).
+SD_DEV void cta_bal_reduce(const Cta& c, double& cs, double& rs, double& cam, int& cai, double& ram, int& rai) {
+#ifdef STAB_EMU
+  (void)c; (void)cs; (void)rs; (void)cam; (void)cai; (void)ram; (void)rai;
+#else
+  for (int o = 16; o > 0; o >>= 1) {
+    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    double ov = __shfl_xor_sync(0xffffffffu, cam, o); int oi = __shfl_xor_sync(0xffffffffu, cai, o);
+    if (ov > cam || (ov == cam && oi < cai)) { cam = ov; cai = oi; }
+    ov = __shfl_xor_sync(0xffffffffu, ram, o); oi = __shfl_xor_sync(0xffffffffu, rai, o);
+    if (ov > ram || (ov == ram && oi < rai)) { ram = ov; rai = oi; }
+  }
+  double* rd = c.red;                       // [nw][4] doubles + [nw][2] ints
+  int* ri = reinterpret_cast<int*>(c.red + 4 * c.nw);
+  cta_sync();
+  if (c.lane == 0) {
+    rd[4 * c.wid] = cs; rd[4 * c.wid + 1] = rs; rd[4 * c.wid + 2] = cam; rd[4 * c.wid + 3] = ram;
+    ri[2 * c.wid] = cai; ri[2 * c.wid + 1] = rai;
+  }
+  cta_sync();
+  double s0 = 0.0, s1 = 0.0, m0 = rd[2], m1 = rd[3]; int i0 = ri[0], i1 = ri[1];
+  for (int w = 0; w < c.nw; ++w) {
+    s0 += rd[4 * w]; s1 += rd[4 * w + 1];
+    if (w > 0) {
+      double ov = rd[4 * w + 2]; int oi = ri[2 * w];
+      if (ov > m0 || (ov == m0 && oi < i0)) { m0 = ov; i0 = oi; }
+      ov = rd[4 * w + 3]; oi = ri[2 * w + 1];
+      if (ov > m1 || (ov == m1 && oi < i1)) { m1 = ov; i1 = oi; }
+    }
+  }
+  cs = s0; rs = s1; cam = m0; cai = i0; ram = m1; rai = i1;
+#endif
+}
+
 // cnt: int workspace of n entries (global or shared).  Returns ilo/ihi through pointers
 // (every thread gets the same values).
 SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, int* cnt, int& ilo_out, int& ihi_out) {
@@ -139,10 +174,7 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
         double m1 = cabs1(a);
         if (m1 > ram) { ram = m1; rai = j; }
       }
-      double d0 = 0.0, d1 = 0.0;
-      cta_sum4(c, cs, rs, d0, d1);
-      cta_argmax(c, cam, cai);
-      cta_argmax(c, ram, rai);
+      cta_bal_reduce(c, cs, rs, cam, cai, ram, rai);      // one fused reduction (two barriers) instead of three
       ca = cabs(A[cai + (size_t)i * lda]);
       ra = cabs(A[i + (size_t)rai * lda]);
       double cn = sqrt(cs), rn = sqrt(rs);

@@ -68,7 +68,17 @@ SD_DEV void cta_gemm_tile(const Cta& c, double* smem, int i0, int j0, int m, int
   const int rowbase = (c.wid % G::WR) * 16, colbase = (c.wid / G::WR) * G::CPW;
   const int lsel = tg >> 1, qsel = tg & 1;
   const int bx = (g & 1) ^ qsel;                 // which component of L the B fragment needs
-  const bool bneg = ((g & 1) == 0) && (qsel == 1);
+  const bool bneg = (((g & 1) == 0) && (qsel == 1)) != (mma && SUB);   // SUB: accumulate C - L*R directly (L negated)
+  if (mma && SUB) {
+    // the accumulators start from C: its loads overlap the operand tile loads instead of trailing the MMAs
+#pragma unroll
+    for (int mt = 0; mt < G::MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < G::NT; ++nt) {
+        const int i = i0 + rowbase + nt * 4 + tg, j = j0 + colbase + mt * 8 + g;
+        if (i < m && j < nc) acc[mt * G::NT + nt] = C[i + (size_t)j * ldc];
+      }
+  }
 #endif
   for (int k0 = 0; k0 < K; k0 += GEMM_KC) {
     for (int idx = c.tid; idx < TM * GEMM_KC; idx += c.nt) {
@@ -126,9 +136,7 @@ SD_DEV void cta_gemm_tile(const Cta& c, double* smem, int i0, int j0, int m, int
       for (int nt = 0; nt < G::NT; ++nt) {
         const int i = i0 + rowbase + nt * 4 + tg, j = j0 + colbase + mt * 8 + g;
         if (i < m && j < nc) {
-          cplx* p = C + i + (size_t)j * ldc;
-          const cplx v = acc[mt * G::NT + nt];
-          *p = SUB ? (*p - v) : v;
+          C[i + (size_t)j * ldc] = acc[mt * G::NT + nt];
         }
       }
 #endif

@@ -16,7 +16,7 @@ namespace {
 thread_local std::string g_err;
 int g_device = -1;
 bool g_inited = false;
-struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; int hess_streams = 1; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
+struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 64; int hess_streams = 1; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
 bool g_qrprof_on = false;
@@ -88,6 +88,9 @@ struct stabgpu_plan {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   std::vector<cudaEvent_t> evA, evB;
+  bool prof_hess = false;                 // record events around every Hessenberg kernel class (bench breakdown)
+  std::vector<cudaEvent_t> pev; size_t pev_n = 0; std::vector<int> pev_cls;
+  float hess_ms[4] = {0, 0, 0, 0};        // panel_step, gemv, gemm, other
   // grid / profile
   DBuf<double> vm, g2, g22, deta, d2eta, D1, D2, Dt2w, h5;
   bool has_h5 = false;
@@ -178,6 +181,15 @@ int launch_hb_gemm(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t
   return 0;
 }
 
+// profile marks: an event after each kernel class (0 panel_step, 1 gemv, 2 gemm/other level-3, 3 start marker)
+static int hmark(stabgpu_plan* pl, cudaStream_t s, int cls) {
+  if (!pl->prof_hess) return 0;
+  if (pl->pev_n == pl->pev.size()) { cudaEvent_t e; CU(cudaEventCreate(&e)); pl->pev.push_back(e); pl->pev_cls.push_back(cls); }
+  pl->pev_cls[pl->pev_n] = cls;
+  CU(cudaEventRecord(pl->pev[pl->pev_n++], s));
+  return 0;
+}
+
 // one panel of the blocked reduction for the matrices [hb.mat0, hb.mat0 + nmat) on stream s;
 // phase 1: the column loop (panel steps + HBM-bound GEMVs), phase 2: the tensor-core block updates
 int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, int p, bool mma, int phase) {
@@ -193,9 +205,12 @@ int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, 
     dim3 ggemv((rows_max + HB_GEMV_ROWS - 1) / HB_GEMV_ROWS, HB_CHUNKS, nmat);
     for (int j = 0; j < HB_NB; ++j) {
       k_hb_panel_step<<<nmat, 256, sm_step, s>>>(hb, p, j);
+      if (hmark(pl, s, 0)) return 1;
       k_hb_gemv<<<ggemv, HB_GEMV_ROWS, sm_gemv, s>>>(hb, p, j);
+      if (hmark(pl, s, 1)) return 1;
     }
     k_hb_panel_step<<<nmat, 256, sm_step, s>>>(hb, p, HB_NB);
+    if (hmark(pl, s, 0)) return 1;
     CU(cudaGetLastError());
     pl->launches += 2 * HB_NB + 1;
     return 0;
@@ -216,6 +231,7 @@ int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, 
     pl->launches += 1;
     if (launch_hb_gemm<HB_LEFT_UPD>(pl, hb, nmat, s, p, (rows_max + 63) / 64, tn, sm64, mma)) return 1;
   }
+  if (hmark(pl, s, 2)) return 1;
   CU(cudaGetLastError());
   return 0;
 }
@@ -237,6 +253,8 @@ int run_hessenberg(stabgpu_plan* pl) {
   }
   const bool mma = g_tune.hess_mode == 1;
   HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0};
+  pl->pev_n = 0;
+  if (hmark(pl, s, 3)) return 1;
   const int half = (g_tune.hess_streams >= 2 && np >= 16) ? (np + 1) / 2 : np;
   HessBatch hb2 = hb; hb2.mat0 = half;
   if (half < np) { CU(cudaEventRecord(pl->evFork, s)); CU(cudaStreamWaitEvent(pl->stream2, pl->evFork, 0)); }
@@ -359,7 +377,7 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(pl->ev[ST_PREP + 1], s));
   {
-    HqrLaunch q; q.W = g_tune.W; q.ns_max = g_tune.ns; q.steps_max = 64;
+    HqrLaunch q; q.W = g_tune.W; q.ns_max = g_tune.ns; q.steps_max = g_tune.qr_steps;
     if (q.W - 2 < 2 * q.ns_max - 1 || q.steps_max < 2 * q.ns_max - 1 || q.W - 2 * q.ns_max - 1 < 4)
       return fail("libstabgpu: invalid QR tuning (window too small for the shift count)");
     size_t sm = hqr_smem_bytes(q);
@@ -461,6 +479,7 @@ int stabgpu_debug_qr_profile(int enable, long long* out16) {
 }
 
 int stabgpu_set_hess_mode(int mode) { g_tune.hess_mode = mode; return 0; }
+int stabgpu_debug_set_qr_steps(int steps) { if (steps > 0) g_tune.qr_steps = steps; return 0; }
 int stabgpu_set_evec_mode(int mode) { g_tune.evec_mode = mode; return 0; }
 
 int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads) {
@@ -533,6 +552,14 @@ int stabgpu_plan_execute(stabgpu_plan* pl) {
     if (run_eigen(pl, 2, 0)) return 1;
   }
   CU(cudaStreamSynchronize(s));
+  if (pl->prof_hess && pl->pev_n > 1) {
+    for (int c = 0; c < 4; ++c) pl->hess_ms[c] = 0.f;
+    for (size_t i = 1; i < pl->pev_n; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, pl->pev[i - 1], pl->pev[i]);
+      pl->hess_ms[pl->pev_cls[i] < 3 ? pl->pev_cls[i] : 3] += t;
+    }
+  }
   for (int i = 0; i < ST_N; ++i) {
     float t = 0.f;
     cudaEventElapsedTime(&t, pl->ev[i], pl->ev[i + 1]);
@@ -569,6 +596,20 @@ long long stabgpu_plan_launch_count(stabgpu_plan* pl) { return pl ? pl->launches
 void* stabgpu_plan_stream(stabgpu_plan* pl) { return pl ? (void*)pl->stream : nullptr; }
 int stabgpu_plan_capacity(stabgpu_plan* pl) { return pl ? pl->cap : 0; }
 
+/* per-kernel-class breakdown of the Hessenberg stage: enable, execute once, read ms[4] = panel_step, gemv, gemm, other */
+int stabgpu_plan_profile_hessenberg(stabgpu_plan* pl, int enable, float* ms4) {
+  if (!pl) return 1;
+  pl->prof_hess = enable != 0;
+  if (ms4) for (int c = 0; c < 4; ++c) ms4[c] = pl->hess_ms[c];
+  return 0;
+}
+
+int stabgpu_plan_ilohi(stabgpu_plan* pl, int* ilohi) {
+  if (!pl || pl->npts < 1 || !ilohi) return fail("libstabgpu: plan_ilohi bad argument");
+  CU(cudaMemcpy(ilohi, pl->ilohi.p, sizeof(int) * 2 * pl->npts, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 void* stabgpu_plan_eig_dev(stabgpu_plan* pl) { return pl ? (void*)pl->eig.p : nullptr; }
 
 int stabgpu_plan_destroy(stabgpu_plan* pl) {
@@ -580,6 +621,7 @@ int stabgpu_plan_destroy(stabgpu_plan* pl) {
   if (pl->evJoin) cudaEventDestroy(pl->evJoin);
   for (auto e : pl->evA) cudaEventDestroy(e);
   for (auto e : pl->evB) cudaEventDestroy(e);
+  for (auto e : pl->pev) cudaEventDestroy(e);
   for (int i = 0; i <= ST_N; ++i) if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
   delete pl;
   return 0;
