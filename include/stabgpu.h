@@ -100,7 +100,8 @@ int stabgpu_zgeev_batch(int n, int batch, const double* A, int want_vectors, dou
 
 /* Stage (4) of the north star: polish one mode of the temporal problem by shift-invert inverse
  * iteration on the pencil (A0 - sigma B0); new functionality (the reference's polishing tool
- * `shoot` is not in the repo).  x0 may be NULL.  Returns lambda, x (n), residual, iterations. */
+ * `shoot` is not in the repo).  x0 may be NULL.  Returns lambda, x (n, scaled as temporal.f90:867-879),
+ * residual ||A0 x - lambda B0 x|| / (||A0 x|| + |lambda| ||B0 x||), iterations. */
 int stabgpu_temporal_polish(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
                             const double* deta, const double* d2eta, const double* alpha, const double* beta,
                             const double* sigma, const double* x0, int max_iters, double tol,

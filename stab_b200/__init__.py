@@ -32,6 +32,7 @@ from .binding import (  # noqa: F401
     spatial_batch,
     temporal_assemble,
     temporal_batch,
+    temporal_polish,
     write_eig_file,
     zgeev_batch,
     debug_stages,

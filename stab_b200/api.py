@@ -41,17 +41,27 @@ class Case:
     d2eta: Optional[np.ndarray] = None
     vm: Optional[np.ndarray] = None
     h5: Optional[np.ndarray] = None
+    g2vm: Optional[np.ndarray] = None     # analytic mean derivatives (ider=0, getmean2.f90), else None
+    g22vm: Optional[np.ndarray] = None
     x_out: float = 0.0
 
     @property
     def ny(self) -> int:
         return self.params.ny
 
-    def load_profile(self, path: str) -> "Case":
-        """sgengrid (sgengrid.f90:15-45) + getmean (getmean.f90:27-111) [+ circh for curve=2]."""
+    def load_profile(self, path: str, first: Optional[str] = None, second: Optional[str] = None) -> "Case":
+        """sgengrid (sgengrid.f90:15-45) + getmean (getmean.f90:27-111) [+ circh for curve=2].
+        With ider=0 the reference calls getmean2 (getmean2.f90:26-187, temporal.f90:99-103), which reads
+        `first.<ind>` / `second.<ind>` and treats them exactly like the profile (same spline, v := 0,
+        constant beyond the table): pass their paths as `first`, `second`."""
         p = self.params
         self.y, self.eta, self.deta, self.d2eta = B.sgengrid(p.ny, p.yi, p.ymax)
         self.vm = B.getmean(B.read_profile(path), self.y)
+        if p.ider == 0:
+            if first is None or second is None:
+                raise B.StabGpuError("ider=0 needs the first.<ind> and second.<ind> derivative tables (getmean2)")
+            self.g2vm = B.getmean(B.read_profile(first), self.y)
+            self.g22vm = B.getmean(B.read_profile(second), self.y)
         self.h5, self.x_out = None, self.x
         if self.itype in (2, 8):
             if p.curve == 2:                      # spatial.f90:112-118
@@ -101,7 +111,7 @@ def _write(case: Case, name: str, itype: int, omega, alpha, beta, eig, evec):
 def temporal(case: Case, name: Optional[str] = "evec.dat", want_vectors: bool = True):
     """temporal.f90:2 for the point (case.alpha, case.beta).  Returns dict(omg, evec, info)."""
     omg, ev, info = B.temporal_batch(case.params, case.vm, case.deta, case.d2eta, [case.alpha], [case.beta],
-                                     want_vectors=want_vectors)
+                                     g2vm=case.g2vm, g22vm=case.g22vm, want_vectors=want_vectors)
     if info[0] != 0:                                  # temporal.f90:776-785,806-809: stop
         raise B.StabGpuError(f"temporal: eigensolver failure, info = {int(info[0])}")
     res = dict(omg=omg[0], evec=None if ev is None else ev[0], info=int(info[0]))
@@ -115,7 +125,7 @@ def spatial(case: Case, name: Optional[str] = "evec.dat", want_vectors: Optional
     if want_vectors is None:
         want_vectors = case.params.ievec == 1
     alp, ev, info = B.spatial_batch(case.params, case.vm, case.deta, case.d2eta, [case.omega], [case.beta], h5=case.h5,
-                                    want_vectors=want_vectors)
+                                    g2vm=case.g2vm, g22vm=case.g22vm, want_vectors=want_vectors)
     res = dict(alp=alp[0], evec=None if ev is None else ev[0], info=int(info[0]))
     if name:
         _write(case, name, 2, case.omega, case.alpha, case.beta, res["alp"], res["evec"])
@@ -136,7 +146,7 @@ def mtemporal(case: Case, amin, amax, ainc, bmin, bmax, binc, outdir: Optional[s
     a, b = B.mtemporal_points(amin, amax, ainc, bmin, bmax, binc)
     lo, hi = B.shard_range(a.size, rank, world)
     omg, ev, info = B.temporal_batch(case.params, case.vm, case.deta, case.d2eta, a[lo:hi] + 0j, b[lo:hi] + 0j,
-                                     want_vectors=want_vectors)
+                                     g2vm=case.g2vm, g22vm=case.g22vm, want_vectors=want_vectors)
     if outdir is not None:
         for k in range(hi - lo):
             _write(case, os.path.join(outdir, makename("eig", lo + k + 1)), 1, case.omega, complex(a[lo + k]),
@@ -152,7 +162,7 @@ def mspatial(case: Case, omin, omax, oinc, bmin, bmax, binc, outdir: Optional[st
     o, b = B.mspatial_points(omin, omax, oinc, bmin, bmax, binc)
     lo, hi = B.shard_range(o.size, rank, world)
     alp, ev, info = B.spatial_batch(case.params, case.vm, case.deta, case.d2eta, o[lo:hi] + 0j, b[lo:hi] + 0j, h5=case.h5,
-                                    want_vectors=want_vectors)
+                                    g2vm=case.g2vm, g22vm=case.g22vm, want_vectors=want_vectors)
     if outdir is not None:
         for k in range(hi - lo):
             _write(case, os.path.join(outdir, makename("eig", lo + k + 1)), 2, complex(o[lo + k]), case.alpha,

@@ -343,6 +343,23 @@ def spatial_assemble(p: Params, vm, deta, d2eta, omega: complex, beta: complex, 
     return tuple(c.T for c in Cs)
 
 
+def temporal_polish(p: Params, vm, deta, d2eta, alpha: complex, beta: complex, sigma: complex, x0=None, max_iters: int = 8,
+                    tol: float = 1e-13, g2vm=None, g22vm=None):
+    """stabgpu_temporal_polish: shift-invert inverse iteration near `sigma` on (A0, B0).
+    Returns (lambda, x (n,), resid, iters)."""
+    vmc, g2c, g22c, de, d2e = _grid_args(p, vm, g2vm, g22vm, deta, d2eta)
+    n = NDOF * p.ny
+    al, be, sg = _c128(alpha), _c128(beta), _c128(sigma)
+    x0c = None if x0 is None else _c128(x0)
+    lam = np.zeros(1, dtype=np.complex128)
+    x = np.empty(n, dtype=np.complex128)
+    resid, iters = C.c_double(0.0), C.c_int(0)
+    _check(lib().stabgpu_temporal_polish(C.byref(p), _ptr(vmc), _ptr(g2c), _ptr(g22c), _ptr(de), _ptr(d2e), _ptr(al), _ptr(be),
+                                         _ptr(sg), _ptr(x0c), max_iters, tol, _ptr(lam), _ptr(x), C.byref(resid), C.byref(iters)),
+           "stabgpu_temporal_polish")
+    return complex(lam[0]), x, resid.value, iters.value
+
+
 def debug_stages(A: np.ndarray):
     """Balanced matrix, scale, ilo, ihi, Hessenberg(+reflectors), tau of one matrix (stage parity tests)."""
     A = np.asarray(A, dtype=np.complex128)

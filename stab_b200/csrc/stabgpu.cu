@@ -786,10 +786,53 @@ int stabgpu_spatial_assemble(const stabgpu_params* p, const double* vm, const do
   return inspect_common(2, p, vm, g2vm, g22vm, deta, d2eta, h5, omega, beta, C0, C1, C2);
 }
 
-int stabgpu_temporal_polish(const stabgpu_params*, const double*, const double*, const double*, const double*, const double*,
-                            const double*, const double*, const double*, const double*, int, double, double*, double*,
-                            double*, int*) {
-  return fail("libstabgpu: stabgpu_temporal_polish is not implemented yet");
+int stabgpu_temporal_polish(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                            const double* deta, const double* d2eta, const double* alpha, const double* beta,
+                            const double* sigma, const double* x0, int max_iters, double tol, double* lambda, double* x,
+                            double* resid, int* iters) {
+  if (ensure_init()) return 1;
+  if (check_params(p)) return 1;
+  if (!vm || !deta || !d2eta || !alpha || !beta || !sigma || !lambda) return fail("libstabgpu: polish bad argument");
+  if (max_iters < 1) max_iters = 8;
+  if (tol <= 0.0) tol = 1e-13;
+  stabgpu_plan* pl = new stabgpu_plan();
+  pl->kind = 1; pl->prm = *p; pl->ny = p->ny; pl->n = 5 * p->ny; pl->N = pl->n; pl->want_vectors = 0;
+  int rc = upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, nullptr);
+  const int ny = p->ny, n = pl->n;
+  const size_t st = (size_t)n * n;
+  DBuf<cplx> coef, blk, A0, B0, K, sv1, sv2, xv, uv, vv;
+  DBuf<int> ipiv;
+  DBuf<double> out4;
+  if (!rc) rc = coef.alloc((size_t)ny * 75) || blk.alloc((size_t)ny * 25) || A0.alloc(st) || B0.alloc(st) || K.alloc(st) || sv1.alloc(1) ||
+                sv2.alloc(1) || xv.alloc(n) || uv.alloc(n) || vv.alloc(n) || ipiv.alloc(n) || out4.alloc(4);
+  if (rc) { stabgpu_plan_destroy(pl); return 1; }
+  cudaMemcpy(sv1.p, alpha, sizeof(cplx), cudaMemcpyHostToDevice);
+  cudaMemcpy(sv2.p, beta, sizeof(cplx), cudaMemcpyHostToDevice);
+  std::vector<cplx> xh(n);
+  for (int i = 0; i < n; ++i) xh[i] = x0 ? mk(x0[2 * i], x0[2 * i + 1]) : mk(1.0, 0.0);
+  cudaMemcpy(xv.p, xh.data(), sizeof(cplx) * n, cudaMemcpyHostToDevice);
+  GridDev g = pl->grid();
+  Phys ph = phys_from(p);
+  SweepDev sw; sw.s1 = sv1.p; sw.s2 = sv2.p; sw.Re = nullptr; sw.Ma = nullptr;
+  k_node_coef_temporal<<<dim3((ny + 63) / 64, 1), 64>>>(g, ph, sw, 0, 0, coef.p, blk.p);
+  k_inspect_temporal<<<(int)((st + 255) / 256), 256>>>(g, coef.p, blk.p, A0.p, B0.p);
+  const size_t sm = 160 * sizeof(double) + (size_t)n * sizeof(cplx);
+  cudaFuncSetAttribute(k_polish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_polish<<<1, 512, sm>>>(A0.p, B0.p, K.p, n, mk(sigma[0], sigma[1]), xv.p, uv.p, vv.p, ipiv.p, max_iters, tol, out4.p);
+  cudaError_t e = cudaDeviceSynchronize();
+  double o[4] = {0, 0, 0, 0};
+  if (e == cudaSuccess) {
+    cudaMemcpy(o, out4.p, sizeof(o), cudaMemcpyDeviceToHost);
+    if (x) cudaMemcpy(x, xv.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost);
+    e = cudaGetLastError();
+  }
+  stabgpu_plan_destroy(pl);
+  if (e != cudaSuccess) return fail(std::string("libstabgpu: ") + cudaGetErrorString(e));
+  lambda[0] = o[0]; lambda[1] = o[1];
+  if (resid) *resid = o[2];
+  if (iters) *iters = (int)o[3];
+  if (o[3] < 0) return fail("libstabgpu: polish: A0 - sigma B0 is exactly singular (sigma is an eigenvalue to working precision; perturb it)");
+  return 0;
 }
 
 }  // extern "C"
