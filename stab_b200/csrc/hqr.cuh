@@ -120,46 +120,53 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
     // time step touch disjoint row / column pairs, so a thread's updates are independent: load all
     // operands, then all the arithmetic, then all the stores (ILP instead of one latency chain per bulge)
     const int ncol = chi + 1;
-    constexpr int NPT = 8;                                  // bulges per thread
+    constexpr int NPT = 8, NH = 4;                          // bulges per thread, processed in halves (register budget: 128)
     const int ngrp = (ns + NPT - 1) / NPT;
     if (ncol * ngrp <= g.nt) {
       const int col = g.tid % ncol, grp = g.tid / ncol;     // also the row index in the right phase
       const bool mine = g.tid < ncol * ngrp;
-      cplx x1[NPT], x2[NPT]; Refl rf[NPT]; int kk[NPT];
 #pragma unroll
-      for (int u = 0; u < NPT; ++u) {
-        const int b = grp + u * ngrp, s = t - 2 * b;
-        kk[u] = -1;
-        rf[u].tau = mk(0.0, 0.0); rf[u].v2 = mk(0.0, 0.0); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
-        if (mine && b < ns && s >= 0 && s <= smax) {
-          const int kl = L + s - g0;
-          if (col >= kl) { kk[u] = kl; rf[u] = cur[b]; x1[u] = S[kl + col * lds]; x2[u] = S[kl + 1 + col * lds]; }
+      for (int h = 0; h < NPT / NH; ++h) {
+        cplx x1[NH], x2[NH]; Refl rf[NH]; int kk[NH];
+#pragma unroll
+        for (int u = 0; u < NH; ++u) {
+          const int b = grp + (h * NH + u) * ngrp, s = t - 2 * b;
+          kk[u] = -1;
+          rf[u].tau = mk(0.0, 0.0); rf[u].v2 = mk(0.0, 0.0); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
+          if (mine && b < ns && s >= 0 && s <= smax) {
+            const int kl = L + s - g0;
+            if (col >= kl) { kk[u] = kl; rf[u] = cur[b]; x1[u] = S[kl + col * lds]; x2[u] = S[kl + 1 + col * lds]; }
+          }
         }
+#pragma unroll
+        for (int u = 0; u < NH; ++u) apply_left(rf[u], x1[u], x2[u]);
+#pragma unroll
+        for (int u = 0; u < NH; ++u)
+          if (kk[u] >= 0) { S[kk[u] + col * lds] = x1[u]; S[kk[u] + 1 + col * lds] = x2[u]; }
       }
-#pragma unroll
-      for (int u = 0; u < NPT; ++u) apply_left(rf[u], x1[u], x2[u]);
-#pragma unroll
-      for (int u = 0; u < NPT; ++u)
-        if (kk[u] >= 0) { S[kk[u] + col * lds] = x1[u]; S[kk[u] + 1 + col * lds] = x2[u]; }
       grp_sync(g);
       CHASE_PROF(11);
       const int row = col;
 #pragma unroll
-      for (int u = 0; u < NPT; ++u) {
-        const int b = grp + u * ngrp, s = t - 2 * b;
-        kk[u] = -1;
-        rf[u].tau = mk(0.0, 0.0); rf[u].v2 = mk(0.0, 0.0); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
-        if (mine && row >= rlo && b < ns && s >= 0 && s <= smax) {
-          const int kl = L + s - g0;
-          int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
-          if (row <= rmax) { kk[u] = kl; rf[u] = cur[b]; x1[u] = S[row + kl * lds]; x2[u] = S[row + (kl + 1) * lds]; }
+      for (int h = 0; h < NPT / NH; ++h) {
+        cplx x1[NH], x2[NH]; Refl rf[NH]; int kk[NH];
+#pragma unroll
+        for (int u = 0; u < NH; ++u) {
+          const int b = grp + (h * NH + u) * ngrp, s = t - 2 * b;
+          kk[u] = -1;
+          rf[u].tau = mk(0.0, 0.0); rf[u].v2 = mk(0.0, 0.0); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
+          if (mine && row >= rlo && b < ns && s >= 0 && s <= smax) {
+            const int kl = L + s - g0;
+            int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
+            if (row <= rmax) { kk[u] = kl; rf[u] = cur[b]; x1[u] = S[row + kl * lds]; x2[u] = S[row + (kl + 1) * lds]; }
+          }
         }
+#pragma unroll
+        for (int u = 0; u < NH; ++u) apply_right(rf[u], x1[u], x2[u]);
+#pragma unroll
+        for (int u = 0; u < NH; ++u)
+          if (kk[u] >= 0) { S[row + kk[u] * lds] = x1[u]; S[row + (kk[u] + 1) * lds] = x2[u]; }
       }
-#pragma unroll
-      for (int u = 0; u < NPT; ++u) apply_right(rf[u], x1[u], x2[u]);
-#pragma unroll
-      for (int u = 0; u < NPT; ++u)
-        if (kk[u] >= 0) { S[row + kk[u] * lds] = x1[u]; S[row + (kk[u] + 1) * lds] = x2[u]; }
       grp_sync(g);
     } else {
       // generic path (small thread groups / many bulges per thread)
@@ -387,10 +394,106 @@ SD_NOINLINE void slab_line(cplx* base, size_t stride, int L, int smax, int ta, i
   }
 }
 
+#ifndef STAB_EMU
+// The same pipeline split over a LANE PAIR (even lane: stages 0..NSB/2-1 and the input stream, odd
+// lane: stages NSB/2..NSB-1 and the output stream); the element crossing the split travels by one
+// warp shuffle per time step.  Halves the registers per thread (two CTAs per SM) at equal work.
+template <int NSB, bool RIGHT, bool STEADY>
+SD_NOINLINE void slab_line_pair(cplx* base, size_t stride, int L, int smax, int ta, int tb, const Refl* rec, unsigned mask, int part) {
+  constexpr int NL = NSB / 2;
+  const int b0 = part * NL;
+  cplx st[NL], pipe[NL];
+#pragma unroll
+  for (int bl = 0; bl < NL; ++bl) {                       // prologue: elements in flight at time ta
+    const int b = b0 + bl, s = ta - 2 * b;
+    st[bl] = mk(0.0, 0.0); pipe[bl] = mk(0.0, 0.0);
+    if (STEADY || (s >= 0 && s <= smax + 1)) st[bl] = base[(size_t)(L + s) * stride];
+    if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) pipe[bl] = base[(size_t)(L + s + 1) * stride];
+  }
+  cplx inq[SLAB_PF];
+#pragma unroll
+  for (int u = 0; u < SLAB_PF; ++u) {
+    const int t = ta + u;
+    inq[u] = (part == 0 && t < tb && t <= smax) ? base[(size_t)(L + t + 1) * stride] : mk(0.0, 0.0);
+  }
+  cplx outp = mk(0.0, 0.0);                               // emission of this lane's last stage at the previous step
+  for (int t0 = ta; t0 < tb; t0 += SLAB_PF) {
+#pragma unroll
+    for (int u = 0; u < SLAB_PF; ++u) {
+      const int t = t0 + u;
+      if (t < tb) {
+        const cplx xin = inq[u];
+        {
+          const int tn = t + SLAB_PF;
+          if (part == 0 && tn < tb && tn <= smax) inq[u] = base[(size_t)(L + tn + 1) * stride];
+        }
+        const cplx got = mk(__shfl_xor_sync(mask, outp.re, 1), __shfl_xor_sync(mask, outp.im, 1));
+        if (part == 1 && t > ta) pipe[0] = got;
+        const Refl* rt = rec + (size_t)(t - ta) * NSB + b0;
+#pragma unroll
+        for (int bb = 0; bb < NL; ++bb) {
+          const int bl = NL - 1 - bb, b = b0 + bl, s = t - 2 * b;
+          if (STEADY || (s >= 0 && s <= smax)) {
+            cplx x1 = st[bl];
+            cplx x2 = (b == 0) ? xin : pipe[bl];
+            const Refl r = rt[bl];
+            if (RIGHT) apply_right(r, x1, x2); else apply_left(r, x1, x2);
+            if (bl == NL - 1) { if (part == 1) base[(size_t)(L + s) * stride] = x1; else outp = x1; }
+            else pipe[bl + 1 < NL ? bl + 1 : bl] = x1;
+            st[bl] = x2;
+          } else if (s == -1) {
+            if (b >= 1) st[bl] = pipe[bl];
+          } else if (s == smax + 1) {
+            if (bl == NL - 1) { if (part == 1) base[(size_t)(L + s) * stride] = st[bl]; else outp = st[bl]; }
+            else pipe[bl + 1 < NL ? bl + 1 : bl] = st[bl];
+          }
+        }
+      }
+    }
+  }
+  {
+    const cplx got = mk(__shfl_xor_sync(mask, outp.re, 1), __shfl_xor_sync(mask, outp.im, 1));
+    if (part == 1 && tb > ta) pipe[0] = got;
+  }
+#pragma unroll
+  for (int bl = 0; bl < NL; ++bl) {                       // epilogue: park the elements still in flight
+    const int b = b0 + bl, s = tb - 2 * b;
+    if (STEADY || (s >= 0 && s <= smax + 1)) base[(size_t)(L + s) * stride] = st[bl];
+    if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) base[(size_t)(L + s + 1) * stride] = pipe[bl];
+  }
+}
+#endif
+
 template <int NSB>
 SD_DEV void slabs_stream(const Cta& c, cplx* H, int ldh, int L, int I, int g0, int g1, int ta, int tb, const Refl* rec) {
   const int smax = I - 1 - L;
   const bool steady = (ta >= 2 * (NSB - 1)) && (tb - 1 <= smax);
+#ifndef STAB_EMU
+  {
+    const int part = c.tid & 1, half = c.nt >> 1;
+    const int nleft = I - g1, nright = g0 - L;              // left slab columns (g1, I], right slab rows [L, g0)
+    for (int base_i = 0; base_i < nleft; base_i += half) {
+      const int li = base_i + (c.tid >> 1);
+      const bool act = li < nleft;
+      const unsigned mask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        cplx* line = H + (size_t)(g1 + 1 + li) * ldh;
+        if (steady) slab_line_pair<NSB, false, true>(line, 1, L, smax, ta, tb, rec, mask, part);
+        else slab_line_pair<NSB, false, false>(line, 1, L, smax, ta, tb, rec, mask, part);
+      }
+    }
+    for (int base_i = 0; base_i < nright; base_i += half) {
+      const int li = base_i + (c.tid >> 1);
+      const bool act = li < nright;
+      const unsigned mask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        cplx* line = H + (L + li);
+        if (steady) slab_line_pair<NSB, true, true>(line, (size_t)ldh, L, smax, ta, tb, rec, mask, part);
+        else slab_line_pair<NSB, true, false>(line, (size_t)ldh, L, smax, ta, tb, rec, mask, part);
+      }
+    }
+  }
+#else
   // left slab: rows of the window, columns (g1, I]; one thread per column
   for (int col = g1 + 1 + c.tid; col <= I; col += c.nt) {
     if (steady) slab_line<NSB, false, true>(H + (size_t)col * ldh, 1, L, smax, ta, tb, rec);
@@ -401,6 +504,7 @@ SD_DEV void slabs_stream(const Cta& c, cplx* H, int ldh, int L, int I, int g0, i
     if (steady) slab_line<NSB, true, true>(H + row, (size_t)ldh, L, smax, ta, tb, rec);
     else slab_line<NSB, true, false>(H + row, (size_t)ldh, L, smax, ta, tb, rec);
   }
+#endif
 }
 
 // One multishift sweep over the active block [L, I] of the global Hessenberg matrix H.

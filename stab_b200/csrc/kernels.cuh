@@ -293,7 +293,7 @@ SD_HD size_t hqr_smem_bytes(const HqrLaunch& q) {
   return b;
 }
 
-__global__ void k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q, long long* prof) {
+__global__ void __launch_bounds__(256, 2) k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q, long long* prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* sp = smem_raw;
   double* red = reinterpret_cast<double*>(sp); sp += 160 * sizeof(double);

@@ -16,7 +16,7 @@ namespace {
 thread_local std::string g_err;
 int g_device = -1;
 bool g_inited = false;
-struct Tuning { int W = 96, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 64; int hess_streams = 1; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
+struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int hess_streams = 1; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
 bool g_qrprof_on = false;
