@@ -83,14 +83,15 @@ SD_DEV void cta_gemm_tile(const Cta& c, double* smem, int i0, int j0, int m, int
   for (int k0 = 0; k0 < K; k0 += GEMM_KC) {
     for (int idx = c.tid; idx < TM * GEMM_KC; idx += c.nt) {
       int i, l;
-      if (LOp::kfast) { l = idx % GEMM_KC; i = idx / GEMM_KC; } else { i = idx % TM; l = idx / TM; }
+      // kfast operands: 4 consecutive k (64 B of memory) x 8 rows per warp -> full sectors AND conflict-free smem stores
+      if (LOp::kfast) { l = (idx & 3) + 4 * (idx / (4 * TM)); i = (idx >> 2) % TM; } else { i = idx % TM; l = idx / TM; }
       cplx v = mk(0.0, 0.0);
       if (i0 + i < m && k0 + l < K) v = L(i0 + i, k0 + l);
       sL[l * G::SLD + 2 * i] = v.re; sL[l * G::SLD + 2 * i + 1] = v.im;
     }
     for (int idx = c.tid; idx < TN * GEMM_KC; idx += c.nt) {
       int j, l;
-      if (ROp::kfast) { l = idx % GEMM_KC; j = idx / GEMM_KC; } else { j = idx % TN; l = idx / TN; }
+      if (ROp::kfast) { l = (idx & 3) + 4 * (idx / (4 * TN)); j = (idx >> 2) % TN; } else { j = idx % TN; l = idx / TN; }
       cplx v = mk(0.0, 0.0);
       if (j0 + j < nc && k0 + l < K) v = R(k0 + l, j0 + j);
       sR[l * G::SRD + 2 * j] = v.re; sR[l * G::SRD + 2 * j + 1] = v.im;

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(HB_GEMV_ROWS) k_hb_gemv(HessBatch hb, int pane
 }
 
 template <int PHASE, bool USE_MMA>
-__global__ void __launch_bounds__(GEMM_THREADS) k_hb_gemm(HessBatch hb, int panel) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2) k_hb_gemm(HessBatch hb, int panel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta c = make_cta(nullptr);
   cta_hb_gemm<PHASE, USE_MMA>(c, hb, hb.mat0 + blockIdx.z, panel, blockIdx.x, blockIdx.y, reinterpret_cast<double*>(smem_raw));
@@ -375,7 +375,7 @@ __global__ void k_evec(const cplx* Hh, size_t hstride, int n, const int* ilohi, 
 
 // back-transformation GEMM phases (hess_blocked.cuh) and the T multiply
 template <int PHASE, bool USE_MMA>
-__global__ void __launch_bounds__(GEMM_THREADS) k_bt_gemm(HessBatch hb, cplx* X, size_t xstride, int panel) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2) k_bt_gemm(HessBatch hb, cplx* X, size_t xstride, int panel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta c = make_cta(nullptr);
   cta_bt_gemm<PHASE, USE_MMA>(c, hb, X, xstride, hb.mat0 + blockIdx.z, panel, blockIdx.x, blockIdx.y, reinterpret_cast<double*>(smem_raw));
