@@ -1104,5 +1104,5 @@ def getevec_text(p_like: dict, eigval: complex, rows: np.ndarray, itype: int) ->
     else:
         out += [cl("Omega", p_like["omega"]), cl("Alpha", eigval), cl("Beta ", p_like["beta"])]
     for r in rows:
-        out.append("".join(_fmt_e21(v) + " " for v in r).rstrip("\n"))
+        out.append("".join(_fmt_e21(v) + " " for v in r).rstrip())   # trailing 1x emits nothing (cf. thesis/TStest/time.ref)
     return "\n".join(out) + "\n"

@@ -38,5 +38,6 @@ from .binding import (  # noqa: F401
     debug_stages,
 )
 from .api import Case, read_deck, spatial, temporal, mtemporal, mspatial  # noqa: F401
+from . import post  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

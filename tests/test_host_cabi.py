@@ -128,3 +128,33 @@ def test_deck_reader_matches_oracle():
         assert (q.Ma, q.Re, q.Pr, q.yi, q.ymax) == (p.Ma, p.Re, p.Pr, p.yi, p.ymax)
         assert (c.itype, c.alpha, c.beta, c.omega, c.ind, c.x) == (p.itype, p.alpha, p.beta, p.omega, p.ind, p.x)
         assert (q.Te, q.rmue, q.rlme, q.cone) == (p.Te, p.rmue, p.rlme, p.cone)
+
+
+def test_post_getevec_text_matches_oracle_and_golden_format():
+    """stab_b200.post reproduces getevec's file (getevec.f90:193-227) character for character vs the oracle's writer,
+    and numerically the reference golden file thesis/TStest/time.ref (abs 1e-8, the reference CI tolerance)."""
+    import io
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0")
+    r = so.run_deck(p, golden_text("ts_profile.0"))
+    target = complex(1.1467880189410E-001, 2.3844535276599E-003)
+    txt = sb.post.getevec_text(1, p.Re, p.Ma, p.Pr, p.omega, p.alpha, p.beta, g["y"], r["omg"], r["evec"], value=target)
+    j = so.select_mode(r["omg"], target)
+    ref_txt = so.getevec_text(dict(Re=p.Re, Ma=p.Ma, Pr=p.Pr, omega=p.omega, alpha=p.alpha, beta=p.beta), r["omg"][j],
+                              so.getevec_rows(g["y"], r["evec"][:, j], p.ny), 1)
+    assert txt == ref_txt
+    mine = np.loadtxt(io.StringIO(txt), comments="#")
+    gold = np.loadtxt(io.StringIO(golden_text("ts_temporal_ny96.time.ref")), comments="#")
+    assert np.abs(mine - gold).max() < 1e-8
+    hdr = txt.splitlines()[1]
+    assert hdr.startswith("# Omega = ( 1.14678801894") and "E-001" in hdr
+
+
+def test_post_mode_tracking():
+    rng = np.random.default_rng(0)
+    prm = np.linspace(0.1, 0.4, 12)
+    mode = 0.3 * prm + 0.01j * (1 - (prm - 0.25) ** 2 * 40)
+    spectra = [np.concatenate([rng.standard_normal(20) + 1j * rng.standard_normal(20) + 3, [m]]) for m in mode]
+    for s in spectra:
+        rng.shuffle(s)
+    assert np.allclose(sb.post.track_nearest(spectra, mode[0]), mode)
+    assert np.allclose(sb.post.track_extrapolated(spectra, prm, mode[0]), mode)
