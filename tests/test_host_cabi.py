@@ -146,7 +146,7 @@ def test_post_getevec_text_matches_oracle_and_golden_format():
     gold = np.loadtxt(io.StringIO(golden_text("ts_temporal_ny96.time.ref")), comments="#")
     assert np.abs(mine - gold).max() < 1e-8
     hdr = txt.splitlines()[1]
-    assert hdr.startswith("# Omega = ( 1.14678801894") and "E-001" in hdr
+    assert hdr.startswith("# Omega = ( 1.146788018") and "E-001" in hdr
 
 
 def test_post_mode_tracking():
