@@ -1,0 +1,71 @@
+!> ISO_C_BINDING interface to libstabgpu (include/stabgpu.h) for stab's Fortran drivers.
+!> Replaces the inside of temporal (temporal.f90:95-879) and spatial (spatial.f90:96-1084);
+!> see INTEGRATION.md for the patched call sites.  Not compiled in this repository's build image
+!> (no Fortran compiler); field order and types mirror `struct stabgpu_params` exactly.
+module stabgpu_mod
+  use iso_c_binding
+  implicit none
+
+  type, bind(C) :: stabgpu_params
+     integer(c_int) :: ny, mattyp, wallt, top, curve, ider, ievec, wall
+     real(c_double) :: Ma, Re, Pr
+     real(c_double) :: gamma, gamma1, cp
+     real(c_double) :: Te, rmue, rlme, cone
+     real(c_double) :: datmat(3)
+     real(c_double) :: yi, ymax, x
+  end type stabgpu_params
+
+  interface
+     integer(c_int) function stabgpu_init(device) bind(C, name='stabgpu_init')
+       import :: c_int
+       integer(c_int), value :: device
+     end function stabgpu_init
+
+     integer(c_int) function stabgpu_finalize() bind(C, name='stabgpu_finalize')
+       import :: c_int
+     end function stabgpu_finalize
+
+     integer(c_int) function stabgpu_temporal_batch(p, vm, g2vm, g22vm, deta, d2eta, npts, alpha, beta, &
+                                                    Re_pt, Ma_pt, want_vectors, omg, evec, info)       &
+                                                    bind(C, name='stabgpu_temporal_batch')
+       import :: c_int, c_double, c_double_complex, c_ptr, stabgpu_params
+       type(stabgpu_params), intent(in) :: p
+       real(c_double), intent(in)  :: vm(*), deta(*), d2eta(*)
+       type(c_ptr), value          :: g2vm, g22vm, Re_pt, Ma_pt
+       integer(c_int), value       :: npts, want_vectors
+       complex(c_double_complex), intent(in)  :: alpha(*), beta(*)
+       complex(c_double_complex), intent(out) :: omg(*)
+       type(c_ptr), value          :: evec
+       integer(c_int), intent(out) :: info(*)
+     end function stabgpu_temporal_batch
+
+     integer(c_int) function stabgpu_spatial_batch(p, vm, g2vm, g22vm, deta, d2eta, h5, npts, omega, beta, &
+                                                   Re_pt, Ma_pt, want_vectors, alp, evec, info)            &
+                                                   bind(C, name='stabgpu_spatial_batch')
+       import :: c_int, c_double, c_double_complex, c_ptr, stabgpu_params
+       type(stabgpu_params), intent(in) :: p
+       real(c_double), intent(in)  :: vm(*), deta(*), d2eta(*)
+       type(c_ptr), value          :: g2vm, g22vm, h5, Re_pt, Ma_pt
+       integer(c_int), value       :: npts, want_vectors
+       complex(c_double_complex), intent(in)  :: omega(*), beta(*)
+       complex(c_double_complex), intent(out) :: alp(*)
+       type(c_ptr), value          :: evec
+       integer(c_int), intent(out) :: info(*)
+     end function stabgpu_spatial_batch
+
+     integer(c_int) function stabgpu_temporal_polish(p, vm, g2vm, g22vm, deta, d2eta, alpha, beta, sigma, x0, &
+                                                     max_iters, tol, lambda, x, resid, iters)                 &
+                                                     bind(C, name='stabgpu_temporal_polish')
+       import :: c_int, c_double, c_double_complex, c_ptr, stabgpu_params
+       type(stabgpu_params), intent(in) :: p
+       real(c_double), intent(in)  :: vm(*), deta(*), d2eta(*)
+       type(c_ptr), value          :: g2vm, g22vm, x0
+       complex(c_double_complex), intent(in)  :: alpha, beta, sigma
+       integer(c_int), value       :: max_iters
+       real(c_double), value       :: tol
+       complex(c_double_complex), intent(out) :: lambda, x(*)
+       real(c_double), intent(out) :: resid
+       integer(c_int), intent(out) :: iters
+     end function stabgpu_temporal_polish
+  end interface
+end module stabgpu_mod

@@ -352,6 +352,32 @@ def test_temporal_ny256_neutral_curve_points():
     assert np.median(d[phys] / np.maximum(np.abs(ref[phys]), 1e-3)) < 1e-10
 
 
+def test_cli_harness_writes_reference_records(tmp_path):
+    """host/stabgpu_cli: `stab < temporal.inp` on the GPU -- stdin deck + profile.<ind> in, evec.dat / eig.<iver> out."""
+    import shutil, subprocess
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stab_b200", "stabgpu_cli")
+    shutil.copy(os.path.join(os.path.dirname(__file__), "golden", "ts_profile.0"), tmp_path / "profile.0")
+    deck = golden_text("ts_temporal_ny96.inp").replace("96", "40", 1)
+    r = subprocess.run([cli], input=deck, capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    back = so.read_eig_file(open(tmp_path / "evec.dat", "rb").read())
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=40)
+    ref = so.solve_temporal(p, g["vm"], g["deta"], g["d2eta"], want_vectors=True)
+    assert back["ny"] == 40 and back["itype"] == 1 and back["alpha"] == p.alpha
+    _, d = match_spectra(ref["omg"], back["eval"])
+    phys = np.abs(ref["omg"]) < 2.0
+    assert (d[phys] / np.maximum(np.abs(ref["omg"][phys]), 1e-3)).max() < 1e-10
+    assert eigpair_residuals(ref["M"], back["eval"], back["evec"]).max() < 1e-11
+    # itype 7: the (alpha, beta) sweep of mtemporal.f90 -> eig.1 .. eig.4
+    lines = deck.splitlines()
+    sweep = lines[:6] + ["7", "0", "0.1 0.5 0.1", "0.0 0.0 1.0"]      # itype 7, ind, alpha range, beta range
+    r = subprocess.run([cli], input="\n".join(sweep) + "\n", capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert sorted(f for f in os.listdir(tmp_path) if f.startswith("eig.")) == ["eig.1", "eig.2", "eig.3", "eig.4"]
+    b3 = so.read_eig_file(open(tmp_path / "eig.3", "rb").read())
+    assert abs(b3["alpha"] - 0.3) < 1e-15 and "evec" not in b3
+
+
 def test_ider0_analytic_derivatives_getmean2(tmp_path):
     """ider=0 (getmean2.f90:26-187, temporal.f90:99-103): the mean derivatives come from first.<ind> /
     second.<ind> tables instead of D1/D2.  Tables here are finite differences of the shipped profile."""

@@ -158,3 +158,17 @@ def test_post_mode_tracking():
         rng.shuffle(s)
     assert np.allclose(sb.post.track_nearest(spectra, mode[0]), mode)
     assert np.allclose(sb.post.track_extrapolated(spectra, prm, mode[0]), mode)
+
+
+def test_cli_harness_fails_loudly_without_gpu(tmp_path):
+    """host/stabgpu_cli (the C++ front end: `stab < temporal.inp`) parses the deck and the profile, then refuses to run
+    without a CUDA device -- no CPU fallback."""
+    import shutil, subprocess, torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cli = os.path.join(ROOT, "stab_b200", "stabgpu_cli")
+    if not os.path.exists(cli):
+        pytest.skip("stabgpu_cli not built")
+    shutil.copy(os.path.join(GOLDEN, "ts_profile.0"), tmp_path / "profile.0")
+    r = subprocess.run([cli], input=golden_text("ts_temporal_ny96.inp"), capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
