@@ -39,8 +39,8 @@ SD_DEV Refl larfg2(cplx& x1, cplx x2) {
   Refl r; r.v2 = mk(0.0, 0.0); r.tau = mk(0.0, 0.0);
   if (is_zero(x2) && x1.im == 0.0) return r;
   const double mx = fmax(cabs1(x1), cabs1(x2));
-  double sc = 1.0;
-  if (mx > 1.0e140 || mx < 1.0e-140) sc = ldexp(1.0, -ilogb(mx));
+  double sc = 1.0, isc = 1.0;                               // power-of-two scale and its exact inverse
+  if (mx > 1.0e140 || mx < 1.0e-140) { const int e = ilogb(mx); sc = ldexp(1.0, -e); isc = ldexp(1.0, e); }
   const cplx a = mk(x1.re * sc, x1.im * sc), b = mk(x2.re * sc, x2.im * sc);
   const double ss = fma(a.re, a.re, fma(a.im, a.im, fma(b.re, b.re, b.im * b.im)));
 #ifdef STAB_EMU
@@ -60,7 +60,7 @@ SD_DEV Refl larfg2(cplx& x1, cplx x2) {
   const double id = __drcp_rn(fma(d.re, d.re, d.im * d.im));
 #endif
   r.v2 = mk((b.re * d.re + b.im * d.im) * id, (b.im * d.re - b.re * d.im) * id);
-  x1 = mk(beta / sc, 0.0);
+  x1 = mk(beta * isc, 0.0);
   return r;
 }
 
@@ -207,6 +207,154 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Chase of a multishift chain inside the shared-memory window, ONE barrier per time step.
+// The work of a time step is partitioned into jobs that touch disjoint entries, so the left and
+// right applications need no barrier between them (a left and a right application commute; the
+// per-entry order left-then-right of `chase` is kept):
+//   * bulge job b (one thread per bulge): the 3x2 block rows k..k+2, cols k..k+1 of bulge b
+//     (left on both columns, right on the three rows) and -- from the two entries it just
+//     produced in registers -- the reflector of the NEXT step, written to the other half of the
+//     double-buffered `cur`; bulges entering at the next step are generated by the same thread;
+//   * tile job (b, b'), b' ahead of b: rows (k_b, k_b+1) x cols (k_b', k_b'+1): left with
+//     reflector b on both columns, right with reflector b' on both rows;
+//   * line jobs: columns right of the chain (left applications only) and rows above it (right
+//     applications only), four consecutive bulges (8 contiguous entries) per job.
+// S is the wsz x wsz window with global origin g0 (rows above the active block are never inside:
+// g0 >= L).  cur holds 2*ns reflectors.  rec receives reflector (t, b) at (t-ta)*ns + b.
+// ---------------------------------------------------------------------------------------------
+SD_DEV Refl zero_refl() { Refl r; r.v2 = mk(0.0, 0.0); r.tau = mk(0.0, 0.0); return r; }
+
+SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, int I,
+                        const cplx* shifts, int ns, int ta, int tb, Refl* rec, Refl* cur) {
+  const int smax = I - 1 - L;
+  const int kb0 = L - g0;                                   // local position of a bulge at s = 0
+  const int ilast = I - g0;                                 // last local row / column of the active block
+  // prologue: reflectors of step ta (as `chase` generates them at the start of a step)
+  {
+    Refl* cb = cur + (ta & 1) * ns;
+    for (int b = g.tid; b < ns; b += g.nt) {
+      const int s = ta - 2 * b;
+      Refl r = zero_refl();
+      if (s >= 0 && s <= smax) {
+        const int kl = kb0 + s;
+        if (s == 0) {
+          cplx x1 = S[kl + kl * lds] - shifts[b];
+          cplx x2 = S[kl + 1 + kl * lds];
+          r = larfg2(x1, x2);
+        } else {
+          cplx x1 = S[kl + (kl - 1) * lds];
+          cplx x2 = S[kl + 1 + (kl - 1) * lds];
+          r = larfg2(x1, x2);
+          S[kl + (kl - 1) * lds] = x1;
+          S[kl + 1 + (kl - 1) * lds] = mk(0.0, 0.0);
+        }
+      }
+      cb[b] = r;
+      rec[b] = r;
+    }
+  }
+  grp_sync(g);
+  const int nbt = (g.nt >= 64) ? 32 : 0;                    // threads reserved for the bulge jobs (first warp)
+  const int ntile = ns * (ns - 1) / 2;
+  for (int t = ta; t < tb; ++t) {
+    const Refl* cb = cur + (t & 1) * ns;
+    Refl* nb = cur + ((t + 1) & 1) * ns;
+    const bool more = (t + 1 < tb);
+    // active bulges at time t: blo..bhi (s = t - 2b in [0, smax])
+    int bhi = t >> 1; if (bhi > ns - 1) bhi = ns - 1;
+    int blo = (t - smax + 1) >> 1; if (blo < 0) blo = 0;     // ceil((t - smax)/2) for t - smax >= 0
+    // ---- bulge jobs ------------------------------------------------------------------------
+    if (g.tid < (nbt ? ns : g.nt)) {
+      for (int b = g.tid; b < ns; b += (nbt ? ns : g.nt)) {
+        const int s = t - 2 * b;
+        Refl rn = zero_refl();
+        if (s >= 0 && s <= smax) {
+          const int k = kb0 + s;
+          const bool has3 = (k + 2 <= ilast);
+          cplx a00 = S[k + k * lds], a10 = S[k + 1 + k * lds];
+          cplx a01 = S[k + (k + 1) * lds], a11 = S[k + 1 + (k + 1) * lds];
+          cplx a20 = mk(0.0, 0.0), a21 = mk(0.0, 0.0);
+          if (has3) { a20 = S[k + 2 + k * lds]; a21 = S[k + 2 + (k + 1) * lds]; }
+          const Refl r = cb[b];
+          apply_left(r, a00, a10); apply_left(r, a01, a11);
+          apply_right(r, a00, a01); apply_right(r, a10, a11);
+          if (has3) apply_right(r, a20, a21);
+          if (more && s + 1 <= smax) {                       // reflector of step t+1 from column k, rows k+1, k+2
+            rn = larfg2(a10, a20);
+            a20 = mk(0.0, 0.0);
+          }
+          S[k + k * lds] = a00; S[k + 1 + k * lds] = a10;
+          S[k + (k + 1) * lds] = a01; S[k + 1 + (k + 1) * lds] = a11;
+          if (has3) { S[k + 2 + k * lds] = a20; S[k + 2 + (k + 1) * lds] = a21; }
+        } else if (s == -1 && more && smax >= 0) {           // bulge b enters at step t+1
+          cplx x1 = S[kb0 + kb0 * lds] - shifts[b];
+          cplx x2 = S[kb0 + 1 + kb0 * lds];
+          rn = larfg2(x1, x2);
+        }
+        nb[b] = rn;
+        if (more) rec[(t + 1 - ta) * ns + b] = rn;
+      }
+    }
+    // ---- tile and line jobs -----------------------------------------------------------------
+    if (blo <= bhi && (nbt == 0 || g.tid >= nbt)) {
+      const int klo = kb0 + t - 2 * blo;                     // position of the leading active bulge
+      const int khi = kb0 + t - 2 * bhi;                     // position of the trailing active bulge
+      const int c0 = klo + 2;                                // first left-only column
+      int nL = wsz - c0; if (nL < 0) nL = 0;
+      if (c0 > ilast) nL = 0;
+      const int nR = khi;                                    // right-only rows 0 .. khi-1
+      const int nq = (ns + 3) >> 2;
+      const int nline = nL + nR;
+      const int njobs = ntile + nline * nq;
+      for (int j = g.tid - nbt; j < njobs; j += g.nt - nbt) {
+        if (j < ntile) {
+          const int p = j / ns, i = j - p * ns;
+          int b, bp;
+          if (i <= p) { b = p + 1; bp = i; } else { b = ns - 1 - p; bp = i - p - 1; }
+          if (bp < blo || b > bhi) continue;
+          const int kr = kb0 + t - 2 * b, kc = kb0 + t - 2 * bp;
+          cplx* q0 = S + kr + kc * lds;
+          cplx a00 = q0[0], a10 = q0[1], a01 = q0[lds], a11 = q0[lds + 1];
+          const Refl rl = cb[b], rr = cb[bp];
+          apply_left(rl, a00, a10); apply_left(rl, a01, a11);
+          apply_right(rr, a00, a01); apply_right(rr, a10, a11);
+          q0[0] = a00; q0[1] = a10; q0[lds] = a01; q0[lds + 1] = a11;
+        } else {
+          const int u = j - ntile;
+          const int q = u / nline, line = u - q * nline;     // consecutive threads: consecutive lines (bank-conflict free)
+          if (line < nL) {                                   // column c0 + line: left applications of bulges 4q .. 4q+3
+            cplx* col = S + (c0 + line) * lds;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int b = 4 * q + e;
+              if (b >= blo && b <= bhi) {
+                const int k = kb0 + t - 2 * b;
+                cplx x1 = col[k], x2 = col[k + 1];
+                apply_left(cb[b], x1, x2);
+                col[k] = x1; col[k + 1] = x2;
+              }
+            }
+          } else {                                           // row (line - nL): right applications of bulges 4q .. 4q+3
+            cplx* row = S + (line - nL);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int b = 4 * q + e;
+              if (b >= blo && b <= bhi) {
+                const int k = kb0 + t - 2 * b;
+                cplx x1 = row[k * lds], x2 = row[(k + 1) * lds];
+                apply_right(cb[b], x1, x2);
+                row[k * lds] = x1; row[(k + 1) * lds] = x2;
+              }
+            }
+          }
+        }
+      }
+    }
+    grp_sync(g);
+  }
+}
+
 // ZLAHQR's small-subdiagonal test at (k, k-1) on a matrix accessed through `at(r,c)`;
 // lo/hi bound the neighbours consulted when both diagonal entries vanish.
 template <class At>
@@ -307,7 +455,7 @@ struct HqrSmem {
   int ldw, W;
   Refl* rec;     // steps_max * ns_max
   int steps_max, ns_max;
-  Refl* cur;     // ns_max
+  Refl* cur;     // 2 * ns_max (double-buffered by chase_tiles)
   cplx* shifts;  // ns_max
   cplx* sm;      // ns_max * (ns_max + 1)   trailing block for the shift computation
   SmallCtl* ctl;
@@ -535,7 +683,7 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
     }
     cta_sync();
     HQR_PROF(2);
-    chase(g, sh.win, ldw, g0, 0, wsz - 1, L, I, sh.shifts, ns, ta, tb, sh.rec, sh.cur, sh.prof);
+    chase_tiles(g, sh.win, ldw, g0, wsz, L, I, sh.shifts, ns, ta, tb, sh.rec, sh.cur);
     HQR_PROF(3);
     for (int q = c.tid; q < wsz * wsz; q += c.nt) {
       const int col = q / wsz, row = q - col * wsz;

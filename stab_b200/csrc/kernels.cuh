@@ -286,7 +286,7 @@ SD_HD size_t hqr_smem_bytes(const HqrLaunch& q) {
   size_t b = 160 * sizeof(double);
   b += (size_t)q.W * (q.W + 1) * sizeof(cplx);
   b += (size_t)q.steps_max * q.ns_max * sizeof(Refl);
-  b += (size_t)q.ns_max * sizeof(Refl);
+  b += (size_t)2 * q.ns_max * sizeof(Refl);
   b += (size_t)q.ns_max * sizeof(cplx);
   b += (size_t)q.ns_max * (q.ns_max + 1) * sizeof(cplx);
   b += sizeof(SmallCtl);
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256, 2) k_hqr(cplx* Hq, size_t hstride, int n,
   sh.W = q.W; sh.ldw = q.W + 1; sh.ns_max = q.ns_max; sh.steps_max = q.steps_max;
   sh.win = reinterpret_cast<cplx*>(sp); sp += (size_t)q.W * (q.W + 1) * sizeof(cplx);
   sh.rec = reinterpret_cast<Refl*>(sp); sp += (size_t)q.steps_max * q.ns_max * sizeof(Refl);
-  sh.cur = reinterpret_cast<Refl*>(sp); sp += (size_t)q.ns_max * sizeof(Refl);
+  sh.cur = reinterpret_cast<Refl*>(sp); sp += (size_t)2 * q.ns_max * sizeof(Refl);
   sh.shifts = reinterpret_cast<cplx*>(sp); sp += (size_t)q.ns_max * sizeof(cplx);
   sh.sm = reinterpret_cast<cplx*>(sp); sp += (size_t)q.ns_max * (q.ns_max + 1) * sizeof(cplx);
   sh.ctl = reinterpret_cast<SmallCtl*>(sp);
