@@ -67,7 +67,9 @@ SD_DEV void cta_bal_reduce(const Cta& c, double& cs, double& rs, double& cam, in
 
 // cnt: int workspace of n entries (global or shared).  Returns ilo/ihi through pointers
 // (every thread gets the same values).
-SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, int* cnt, int& ilo_out, int& ihi_out) {
+// wsp: double workspace of balance_wsp_doubles(n, bal_b) entries (shared memory on the device).
+SD_HD size_t balance_wsp_doubles(int n, int bal_b) { return (size_t)2 * n + (size_t)2 * bal_b * n + 2; }
+SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, int* cnt, double* wsp, int bal_b, int& ilo_out, int& ihi_out) {
   int k = 0;      // first active index
   int l = n;      // one past last active index
   // ---- row isolation: push rows with zero off-diagonal part (within columns [0,l)) down ----
@@ -147,60 +149,124 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
     }
   }
   // ---- scaling of the active block [k, l) ----
-  for (int i = k + c.tid; i < l; i += c.nt) scale[i] = 1.0;
+  // ZGEBAL's loop is Gauss-Seidel over i (each decision sees every scaling made before it).
+  // Scaling by powers of two is exact, so the loop runs on the UNSCALED matrix: |a|^2 of bal_b
+  // columns / rows at a time is staged in shared memory with coalesced, batched loads, one warp
+  // takes the bal_b decisions in order, weighting every entry with the cumulative factors chosen
+  // so far (fs = scale, fi = 1/scale), and the matrix itself is rescaled once at the end by a
+  // single coalesced pass.  Same decisions as the entry-by-entry loop, without two block
+  // reductions, three barriers and a strided row pass per index.
+  double* fs = wsp;                       // n: cumulative column factor (1 outside [k,l))
+  double* fi = wsp + n;                   // n: its exact inverse (row factor)
+  double* cbuf = wsp + 2 * n;             // bal_b x n : |A(r, i_e)|^2
+  double* rbuf = cbuf + (size_t)bal_b * n;   // bal_b x n : |A(i_e, j)|^2
+  int* flag = reinterpret_cast<int*>(rbuf + (size_t)bal_b * n);
+  int lb = 0; while ((1 << (lb + 1)) <= bal_b) ++lb;   // bal_b is a power of two
+  const int B = 1 << lb;
+  for (int i = c.tid; i < n; i += c.nt) { fs[i] = 1.0; fi[i] = 1.0; }
   cta_sync();
   const double radix = 2.0, factor = 0.95;
   const double sfmin1 = SD_SAFMIN / SD_ULP, sfmax1 = 1.0 / sfmin1;
   const double sfmin2 = sfmin1 * 2.0, sfmax2 = 1.0 / sfmin2;
+  constexpr int U = 8;                    // loads in flight per thread
   noconv = true;
   int guard = 0;
   while (noconv && guard++ < 200) {
-    noconv = false;
-    for (int i = k; i < l; ++i) {
-      // column i: c = ||A(k:l, i)||_2, ca = max |A(0:l, i)| ; row i: r = ||A(i, k:l)||_2, ra = max |A(i, k:n)|
-      double cs = 0.0, rs = 0.0, ca = 0.0, ra = 0.0;
-      // IZAMAX picks by |re|+|im| but the value used is the true modulus of that entry; the two
-      // orderings can differ, so track (cabs1, index) then evaluate |.| of the winner.
-      double cam = -1.0, ram = -1.0; int cai = 0, rai = 0;
+    if (c.tid == 0) *flag = 0;
+    for (int i0 = k; i0 < l; i0 += B) {
+      const int nb = (l - i0 < B) ? (l - i0) : B;
+      // stage |a|^2: columns i0..i0+nb-1 (rows 0..l-1), rows i0..i0+nb-1 (columns k..n-1)
       for (int r = c.tid; r < l; r += c.nt) {
-        cplx a = A[r + (size_t)i * lda];
-        if (r >= k) cs += abs2(a);
-        double m1 = cabs1(a);
-        if (m1 > cam) { cam = m1; cai = r; }
+        double v[U];
+#pragma unroll
+        for (int e = 0; e < U; ++e) v[e] = (e < nb) ? abs2(A[r + (size_t)(i0 + e) * lda]) : 0.0;
+#pragma unroll
+        for (int e = 0; e < U; ++e) if (e < nb) cbuf[(size_t)e * n + r] = v[e];
       }
-      for (int j = k + c.tid; j < n; j += c.nt) {
-        cplx a = A[i + (size_t)j * lda];
-        if (j < l) rs += abs2(a);
-        double m1 = cabs1(a);
-        if (m1 > ram) { ram = m1; rai = j; }
+      const int totr = (n - k) << lb;
+      for (int q0 = c.tid; q0 < totr; q0 += c.nt * U) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int q = q0 + u * c.nt, e = q & (B - 1), j = k + (q >> lb);   // e fastest: B consecutive rows of one column
+          v[u] = (q < totr && e < nb) ? abs2(A[(i0 + e) + (size_t)j * lda]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int q = q0 + u * c.nt, e = q & (B - 1), j = k + (q >> lb);
+          if (q < totr && e < nb) rbuf[(size_t)e * n + j] = v[u];
+        }
       }
-      cta_bal_reduce(c, cs, rs, cam, cai, ram, rai);      // one fused reduction (two barriers) instead of three
-      ca = cabs(A[cai + (size_t)i * lda]);
-      ra = cabs(A[i + (size_t)rai * lda]);
-      double cn = sqrt(cs), rn = sqrt(rs);
-      if (cn == 0.0 || rn == 0.0) continue;
-      double g = rn / radix, f = 1.0, s = cn + rn;
-      while (cn < g && fmax(f, fmax(cn, ca)) < sfmax2 && fmin(rn, fmin(g, ra)) > sfmin2) {
-        f *= radix; cn *= radix; ca *= radix; rn /= radix; g /= radix; ra /= radix;
-      }
-      g = cn / radix;
-      while (g >= rn && fmax(rn, ra) < sfmax2 && fmin(fmin(f, cn), fmin(g, ca)) > sfmin2) {
-        f /= radix; cn /= radix; g /= radix; ca /= radix; rn *= radix; ra *= radix;
-      }
-      if ((cn + rn) >= factor * s) continue;
-      double sc = scale[i];
-      if (f < 1.0 && sc < 1.0 && f * sc <= sfmin1) continue;
-      if (f > 1.0 && sc > 1.0 && sc >= sfmax1 / f) continue;
-      g = 1.0 / f;
-      noconv = true;
-      cta_sync();                       // everyone has read scale[i] / pivots before we modify
-      if (c.tid == 0) scale[i] = sc * f;
-      for (int j = k + c.tid; j < n; j += c.nt) A[i + (size_t)j * lda] = A[i + (size_t)j * lda] * g;
       cta_sync();
-      for (int r = c.tid; r < l; r += c.nt) A[r + (size_t)i * lda] = A[r + (size_t)i * lda] * f;
+      if (c.wid == 0) {
+        for (int e = 0; e < nb; ++e) {
+          const int i = i0 + e;
+          const double* cb = cbuf + (size_t)e * n;
+          const double* rb = rbuf + (size_t)e * n;
+          // column i: c = ||A(k:l, i)||_2, ca = max |A(0:l, i)| ; row i: r = ||A(i, k:l)||_2, ra = max |A(i, k:n)|
+          double cs = 0.0, rs = 0.0, cam = 0.0, ram = 0.0;
+          for (int r = c.lane; r < l; r += c.ws) {
+            const double w = fi[r];                           // row factors chosen so far (1 for r < k)
+            const double v = cb[r] * (w * w);
+            if (r >= k) cs += v;
+            cam = fmax(cam, v);
+          }
+          for (int j = k + c.lane; j < n; j += c.ws) {
+            const double w = fs[j];                           // column factors chosen so far (1 for j >= l)
+            const double v = rb[j] * (w * w);
+            if (j < l) rs += v;
+            ram = fmax(ram, v);
+          }
+          cs = warp_sum(cs); rs = warp_sum(rs); cam = warp_max(cam); ram = warp_max(ram);
+          const double sc = fs[i], isc = fi[i];
+          cs *= sc * sc; cam *= sc * sc; rs *= isc * isc; ram *= isc * isc;   // this index's own factors (exact)
+          double ca = sqrt(cam), ra = sqrt(ram);
+          double cn = sqrt(cs), rn = sqrt(rs);
+          if (cn == 0.0 || rn == 0.0) continue;
+          double g = rn / radix, f = 1.0, sum = cn + rn;
+          while (cn < g && fmax(f, fmax(cn, ca)) < sfmax2 && fmin(rn, fmin(g, ra)) > sfmin2) {
+            f *= radix; cn *= radix; ca *= radix; rn /= radix; g /= radix; ra /= radix;
+          }
+          g = cn / radix;
+          while (g >= rn && fmax(rn, ra) < sfmax2 && fmin(fmin(f, cn), fmin(g, ca)) > sfmin2) {
+            f /= radix; cn /= radix; g /= radix; ca /= radix; rn *= radix; ra *= radix;
+          }
+          if ((cn + rn) >= factor * sum) continue;
+          if (f < 1.0 && sc < 1.0 && f * sc <= sfmin1) continue;
+          if (f > 1.0 && sc > 1.0 && sc >= sfmax1 / f) continue;
+          warp_sync();
+          if (c.lane == 0) { fs[i] = sc * f; fi[i] = isc / f; *flag = 1; }
+          warp_sync();
+        }
+      }
       cta_sync();
     }
+    noconv = (*flag != 0);
+#ifdef STAB_EMU_TRACE
+    fprintf(stderr, "balance sweep %d k=%d l=%d noconv=%d\n", guard, k, l, (int)noconv);
+#endif
+    cta_sync();
   }
+  // apply: column j in [k,l) scaled by fs[j] over rows 0..l-1, row r in [k,l) by fi[r] over columns k..n-1
+  for (int i = k + c.tid; i < l; i += c.nt) scale[i] = fs[i];
+  for (int j0 = k; j0 < n; j0 += 4) {
+    for (int r = c.tid; r < l; r += c.nt) {
+      const double fr = (r >= k) ? fi[r] : 1.0;
+      cplx v[4]; double w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        w[u] = (j < n) ? ((j < l) ? fs[j] : 1.0) * fr : 1.0;
+        if (j < n && w[u] != 1.0) v[u] = A[r + (size_t)j * lda];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        if (j < n && w[u] != 1.0) A[r + (size_t)j * lda] = v[u] * w[u];
+      }
+    }
+  }
+  cta_sync();
   ilo_out = k;
   ihi_out = l - 1;
 }

@@ -187,12 +187,14 @@ __global__ void __launch_bounds__(512) k_polish(const cplx* A0, const cplx* B0, 
 }
 
 // ---- stage 3a: balance --------------------------------------------------------------------------
-__global__ void k_balance(cplx* A, size_t astride, int n, double* scale, int* cnt, int* ilohi) {
+SD_HD int balance_block(int n) { const int b = (80 * 1024) / (16 * n); return b >= 8 ? 8 : (b >= 4 ? 4 : (b >= 2 ? 2 : 1)); }   // power of two
+__global__ void __launch_bounds__(256, 2) k_balance(cplx* A, size_t astride, int n, double* scale, int* cnt, int* ilohi, int bal_b) {
   __shared__ double red[160];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta c = make_cta(red);
   const int p = blockIdx.x;
   int ilo, ihi;
-  cta_balance(c, A + (size_t)p * astride, n, n, scale + (size_t)p * n, cnt + (size_t)p * n, ilo, ihi);
+  cta_balance(c, A + (size_t)p * astride, n, n, scale + (size_t)p * n, cnt + (size_t)p * n, reinterpret_cast<double*>(smem_raw), bal_b, ilo, ihi);
   if (threadIdx.x == 0) { ilohi[2 * p] = ilo; ilohi[2 * p + 1] = ihi; }
 }
 

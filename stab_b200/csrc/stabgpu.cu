@@ -367,7 +367,12 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   const int N = pl->N, np = pl->npts;
   const size_t st = (size_t)N * N;
   cudaStream_t s = pl->stream;
-  k_balance<<<np, 256, 0, s>>>(pl->A.p, st, N, pl->scale.p, pl->cnt.p, pl->ilohi.p);
+  {
+    const int bb = balance_block(N);
+    const size_t smb = balance_wsp_doubles(N, bb) * sizeof(double);
+    CU(cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+    k_balance<<<np, 256, smb, s>>>(pl->A.p, st, N, pl->scale.p, pl->cnt.p, pl->ilohi.p, bb);
+  }
   CU(cudaGetLastError());
   CU(cudaEventRecord(pl->ev[ST_BAL + 1], s));
   if (run_hessenberg(pl)) return 1;
@@ -716,7 +721,12 @@ int stabgpu_debug_stages(int n, const double* A, double* balanced, double* scale
   const size_t st = (size_t)n * n;
   cudaStream_t s = pl->stream;
   cudaMemcpy(pl->A.p, A, sizeof(cplx) * st, cudaMemcpyHostToDevice);
-  k_balance<<<1, 256, 0, s>>>(pl->A.p, st, n, pl->scale.p, pl->cnt.p, pl->ilohi.p);
+  {
+    const int bb = balance_block(n);
+    const size_t smb = balance_wsp_doubles(n, bb) * sizeof(double);
+    cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    k_balance<<<1, 256, smb, s>>>(pl->A.p, st, n, pl->scale.p, pl->cnt.p, pl->ilohi.p, bb);
+  }
   cudaStreamSynchronize(s);
   int lh[2];
   cudaMemcpy(lh, pl->ilohi.p, sizeof(lh), cudaMemcpyDeviceToHost);

@@ -20,7 +20,9 @@ int emu_balance(cplx* A, int n, double* scale, int* ilo, int* ihi) {
   std::vector<double> red(256);
   std::vector<int> cnt(n);
   Cta c = make_cta(red.data());
-  cta_balance(c, A, n, n, scale, cnt.data(), *ilo, *ihi);
+  const int bb = 4;
+  std::vector<double> wsp(balance_wsp_doubles(n, bb));
+  cta_balance(c, A, n, n, scale, cnt.data(), wsp.data(), bb, *ilo, *ihi);
   return 0;
 }
 
