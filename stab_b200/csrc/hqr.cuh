@@ -546,17 +546,45 @@ SD_NOINLINE void slab_line(cplx* base, size_t stride, int L, int smax, int ta, i
 // The same pipeline split over a LANE PAIR (even lane: stages 0..NSB/2-1 and the input stream, odd
 // lane: stages NSB/2..NSB-1 and the output stream); the element crossing the split travels by one
 // warp shuffle per time step.  Halves the registers per thread (two CTAs per SM) at equal work.
+//
+// Register roles alternate with the parity of the step instead of being copied: a stage's resident
+// element lives in A[bl] and its input arrives in B[bl]; after the update the emitted value is
+// WRITTEN (as the result of the arithmetic, not copied) to A[bl+1], which the next stage has just
+// vacated, and the kept value stays in B[bl] -- so at the next step B holds the resident elements
+// and A the inputs.  One step:
+template <int NL, bool RIGHT, bool STEADY>
+SD_DEV void slab_pair_step(cplx (&A)[NL], cplx (&B)[NL], cplx& outp, const Refl* __restrict__ rt, int part, int b0, int t,
+                           int L, int smax, cplx* base, size_t stride) {
+#pragma unroll
+  for (int bb = 0; bb < NL; ++bb) {
+    const int bl = NL - 1 - bb, b = b0 + bl, s = t - 2 * b;    // descending: stage bl+1 has vacated A[bl+1]
+    if (STEADY || (s >= 0 && s <= smax)) {
+      cplx x1 = A[bl];
+      cplx x2 = B[bl];
+      const Refl r = rt[bl];
+      if (RIGHT) apply_right(r, x1, x2); else apply_left(r, x1, x2);   // tau = 0 is an exact identity
+      if (bl == NL - 1) { if (part == 1) base[(size_t)(L + s) * stride] = x1; else outp = x1; }
+      else A[bl + 1 < NL ? bl + 1 : bl] = x1;
+      B[bl] = x2;
+    } else if (s == smax + 1) {                                 // flush the resident element
+      if (bl == NL - 1) { if (part == 1) base[(size_t)(L + s) * stride] = A[bl]; else outp = A[bl]; }
+      else A[bl + 1 < NL ? bl + 1 : bl] = A[bl];
+    }                                                           // s == -1: the arrived element (B[bl]) becomes resident by the role swap
+  }
+}
+
 template <int NSB, bool RIGHT, bool STEADY>
 SD_NOINLINE void slab_line_pair(cplx* base, size_t stride, int L, int smax, int ta, int tb, const Refl* rec, unsigned mask, int part) {
   constexpr int NL = NSB / 2;
+  static_assert(SLAB_PF % 2 == 0, "the role alternation needs an even unroll");
   const int b0 = part * NL;
-  cplx st[NL], pipe[NL];
+  cplx P[NL], Q[NL];                                        // at even (t - ta): P resident, Q input; odd: swapped
 #pragma unroll
   for (int bl = 0; bl < NL; ++bl) {                       // prologue: elements in flight at time ta
     const int b = b0 + bl, s = ta - 2 * b;
-    st[bl] = mk(0.0, 0.0); pipe[bl] = mk(0.0, 0.0);
-    if (STEADY || (s >= 0 && s <= smax + 1)) st[bl] = base[(size_t)(L + s) * stride];
-    if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) pipe[bl] = base[(size_t)(L + s + 1) * stride];
+    P[bl] = mk(0.0, 0.0); Q[bl] = mk(0.0, 0.0);
+    if (STEADY || (s >= 0 && s <= smax + 1)) P[bl] = base[(size_t)(L + s) * stride];
+    if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) Q[bl] = base[(size_t)(L + s + 1) * stride];
   }
   cplx inq[SLAB_PF];
 #pragma unroll
@@ -576,38 +604,34 @@ SD_NOINLINE void slab_line_pair(cplx* base, size_t stride, int L, int smax, int 
           if (part == 0 && tn < tb && tn <= smax) inq[u] = base[(size_t)(L + tn + 1) * stride];
         }
         const cplx got = mk(__shfl_xor_sync(mask, outp.re, 1), __shfl_xor_sync(mask, outp.im, 1));
-        if (part == 1 && t > ta) pipe[0] = got;
         const Refl* rt = rec + (size_t)(t - ta) * NSB + b0;
-#pragma unroll
-        for (int bb = 0; bb < NL; ++bb) {
-          const int bl = NL - 1 - bb, b = b0 + bl, s = t - 2 * b;
-          if (STEADY || (s >= 0 && s <= smax)) {
-            cplx x1 = st[bl];
-            cplx x2 = (b == 0) ? xin : pipe[bl];
-            const Refl r = rt[bl];
-            if (RIGHT) apply_right(r, x1, x2); else apply_left(r, x1, x2);
-            if (bl == NL - 1) { if (part == 1) base[(size_t)(L + s) * stride] = x1; else outp = x1; }
-            else pipe[bl + 1 < NL ? bl + 1 : bl] = x1;
-            st[bl] = x2;
-          } else if (s == -1) {
-            if (b >= 1) st[bl] = pipe[bl];
-          } else if (s == smax + 1) {
-            if (bl == NL - 1) { if (part == 1) base[(size_t)(L + s) * stride] = st[bl]; else outp = st[bl]; }
-            else pipe[bl + 1 < NL ? bl + 1 : bl] = st[bl];
-          }
+        if ((u & 1) == 0) {
+          if (part == 0) Q[0] = xin; else if (t > ta) Q[0] = got;
+          slab_pair_step<NL, RIGHT, STEADY>(P, Q, outp, rt, part, b0, t, L, smax, base, stride);
+        } else {
+          if (part == 0) P[0] = xin; else P[0] = got;
+          slab_pair_step<NL, RIGHT, STEADY>(Q, P, outp, rt, part, b0, t, L, smax, base, stride);
         }
       }
     }
   }
-  {
-    const cplx got = mk(__shfl_xor_sync(mask, outp.re, 1), __shfl_xor_sync(mask, outp.im, 1));
-    if (part == 1 && tb > ta) pipe[0] = got;
-  }
+  const cplx got = mk(__shfl_xor_sync(mask, outp.re, 1), __shfl_xor_sync(mask, outp.im, 1));
+  if (((tb - ta) & 1) == 0) {
+    if (part == 1 && tb > ta) Q[0] = got;
 #pragma unroll
-  for (int bl = 0; bl < NL; ++bl) {                       // epilogue: park the elements still in flight
-    const int b = b0 + bl, s = tb - 2 * b;
-    if (STEADY || (s >= 0 && s <= smax + 1)) base[(size_t)(L + s) * stride] = st[bl];
-    if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) base[(size_t)(L + s + 1) * stride] = pipe[bl];
+    for (int bl = 0; bl < NL; ++bl) {                     // epilogue: park the elements still in flight
+      const int b = b0 + bl, s = tb - 2 * b;
+      if (STEADY || (s >= 0 && s <= smax + 1)) base[(size_t)(L + s) * stride] = P[bl];
+      if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) base[(size_t)(L + s + 1) * stride] = Q[bl];
+    }
+  } else {
+    if (part == 1) P[0] = got;
+#pragma unroll
+    for (int bl = 0; bl < NL; ++bl) {
+      const int b = b0 + bl, s = tb - 2 * b;
+      if (STEADY || (s >= 0 && s <= smax + 1)) base[(size_t)(L + s) * stride] = Q[bl];
+      if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) base[(size_t)(L + s + 1) * stride] = P[bl];
+    }
   }
 }
 #endif
