@@ -22,6 +22,7 @@ namespace stab {
 constexpr int HB_NB = 32;         // panel width
 constexpr int HB_CHUNKS = 4;      // column chunks of the GEMV (deterministic split-K)
 constexpr int HB_GEMV_ROWS = 128; // rows per GEMV CTA
+constexpr int HB_DU = 5;          // loads in flight per lane in the panel-step dot products
 
 struct HessBatch {
   cplx* A; size_t astride; int n;
@@ -43,8 +44,8 @@ SD_DEV cplx hb_v(const cplx* A, int lda, int k, int ihi, int r, int l) {   // V(
 }
 
 // One CTA per matrix.  Call j = 0..NB-1 before the GEMV of column j; call j = NB after the last
-// GEMV of the panel.  smem: 160 doubles (reductions) + n + 2*NB complex.
-SD_DEV void cta_hb_panel_step(const Cta& c, const HessBatch& hb, int mat, int panel, int j, double* red, cplx* sb, cplx* sw, cplx* st) {
+// GEMV of the panel.  smem: 160 doubles (reductions) + n + 3*NB complex.
+SD_DEV void cta_hb_panel_step(const Cta& c, const HessBatch& hb, int mat, int panel, int j, double* red, cplx* sb, cplx* sw, cplx* st, cplx* sc) {
   const int n = hb.n, lda = n;
   cplx* A = hb.A + (size_t)mat * hb.astride;
   const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
@@ -62,62 +63,86 @@ SD_DEV void cta_hb_panel_step(const Cta& c, const HessBatch& hb, int mat, int pa
     for (int q = c.tid; q < HB_NB * HB_NB; q += c.nt) T[q] = mk(0.0, 0.0);
     cta_sync();
   }
-  // ---- finish column jp = j-1: Y(:,jp), T(:,jp) (ZLAHR2's post-GEMV part) ----
+  // ---- finish column jp = j-1: Y(:,jp), T(:,jp) (ZLAHR2's post-GEMV part), fused with the first update of
+  // column `col` (b -= Y(:,0:j) conj(V(col,0:j))^T): ONE pass over the rows of Y serves both ----
+  const int col = k + j;
+  const bool have_col = (j < HB_NB) && (col < n);
+  cplx* acol = A + (size_t)col * lda;
+  const int nr = ihi - k;                                   // rows k+1..ihi, local index r-(k+1)
   if (j > 0) {
     const int jp = j - 1, cp = k + jp;
-    if (cp < ihi) {
-      const cplx taup = tau[cp];
+    const bool fin = cp < ihi;
+    const cplx taup = fin ? tau[cp] : mk(0.0, 0.0);
+    if (fin) {
       const cplx* vcol = A + (size_t)cp * lda;
       for (int l = c.wid; l < jp; l += c.nw) {             // t = V(:,0:jp)^H v_jp
         const cplx* vl = A + (size_t)(k + l) * lda;
         cplx s = mk(0.0, 0.0);
-        for (int r = cp + 1 + c.lane; r <= ihi; r += c.ws) {
-          const cplx vr = (r == cp + 1) ? mk(1.0, 0.0) : vcol[r];
-          fma_acc_conj(s, vl[r], vr);
+        for (int r0 = cp + 1 + c.lane; r0 <= ihi; r0 += HB_DU * c.ws) {   // HB_DU loads in flight per operand
+          cplx a[HB_DU], b[HB_DU];
+#pragma unroll
+          for (int u = 0; u < HB_DU; ++u) {
+            const int r = r0 + u * c.ws;
+            a[u] = (r <= ihi) ? vl[r] : mk(0.0, 0.0);
+            b[u] = (r <= ihi) ? ((r == cp + 1) ? mk(1.0, 0.0) : vcol[r]) : mk(0.0, 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < HB_DU; ++u) fma_acc_conj(s, a[u], b[u]);
         }
         s = warp_sum(s);
         if (c.lane == 0) st[l] = s;
       }
-      cta_sync();
-      for (int r = k + 1 + c.tid; r <= ihi; r += c.nt) {   // Y(:,jp) = tau (A v - Y(:,0:jp) t)
+    }
+    if (have_col)
+      for (int l = c.tid; l < j; l += c.nt) sc[l] = conj(hb_v(A, lda, k, ihi, col, l));
+    cta_sync();
+    for (int r = k + 1 + c.tid; r <= ihi; r += c.nt) {
+      cplx yjp = mk(0.0, 0.0);
+      cplx b = have_col ? acol[r] : mk(0.0, 0.0);
+      if (fin) {                                            // Y(:,jp) = tau (A v - Y(:,0:jp) t)
         cplx s = mk(0.0, 0.0);
         for (int ch = 0; ch < HB_CHUNKS; ++ch) s += Yp[r + (size_t)ch * n];
-        for (int l = 0; l < jp; ++l) s -= Y[r + (size_t)l * n] * st[l];
-        Y[r + (size_t)jp * n] = taup * s;
+#pragma unroll 4
+        for (int l = 0; l < jp; ++l) {
+          const cplx y = Y[r + (size_t)l * n];
+          s -= y * st[l];
+          b -= y * sc[l];
+        }
+        yjp = taup * s;
+      } else if (have_col) {
+        for (int l = 0; l < jp; ++l) b -= Y[r + (size_t)l * n] * sc[l];
       }
+      Y[r + (size_t)jp * n] = yjp;
+      if (have_col) { b -= yjp * sc[jp]; sb[r - (k + 1)] = b; }   // b -= Y(:,0:j) conj(V(col,0:j))^T
+    }
+    if (fin) {
       for (int l = c.tid; l <= jp; l += c.nt) {            // T(0:jp,jp) = -tau T(0:jp,0:jp) t ; T(jp,jp) = tau
         if (l == jp) { T[l + jp * HB_NB] = taup; continue; }
         cplx s = mk(0.0, 0.0);
         for (int m = l; m < jp; ++m) fma_acc(s, T[l + m * HB_NB], st[m]);
         T[l + jp * HB_NB] = -(taup * s);
       }
-    } else {
-      for (int r = k + 1 + c.tid; r <= ihi; r += c.nt) Y[r + (size_t)jp * n] = mk(0.0, 0.0);
     }
     cta_sync();
   }
-  if (j >= HB_NB) return;
-  const int col = k + j;
-  if (col >= n) return;
-  // ---- column `col`: apply the panel's previous reflectors (right then left), then generate H(col) ----
-  cplx* acol = A + (size_t)col * lda;
-  const int nr = ihi - k;                                   // rows k+1..ihi, local index r-(k+1)
+  if (!have_col) return;
+  // ---- column `col`: the panel's previous reflectors from the left, then generate H(col) ----
   if (j > 0) {
-    for (int q = c.tid; q < nr; q += c.nt) sb[q] = acol[k + 1 + q];
-    for (int l = c.tid; l < j; l += c.nt) sw[l] = conj(hb_v(A, lda, k, ihi, col, l));
-    cta_sync();
-    for (int q = c.tid; q < nr; q += c.nt) {                // b -= Y(:,0:j) conj(V(col,0:j))^T
-      cplx s = sb[q];
-      for (int l = 0; l < j; ++l) s -= Y[k + 1 + q + (size_t)l * n] * sw[l];
-      sb[q] = s;
-    }
-    cta_sync();
     for (int l = c.wid; l < j; l += c.nw) {                 // w = V^H b
       const cplx* vl = A + (size_t)(k + l) * lda;
       cplx s = mk(0.0, 0.0);
-      for (int r = k + l + 1 + c.lane; r <= ihi; r += c.ws) {
-        const cplx vr = (r == k + l + 1) ? mk(1.0, 0.0) : vl[r];
-        fma_acc_conj(s, vr, sb[r - (k + 1)]);
+      for (int r0 = k + l + 1 + c.lane; r0 <= ihi; r0 += HB_DU * c.ws) {
+        cplx a[HB_DU];
+#pragma unroll
+        for (int u = 0; u < HB_DU; ++u) {
+          const int r = r0 + u * c.ws;
+          a[u] = (r <= ihi) ? ((r == k + l + 1) ? mk(1.0, 0.0) : vl[r]) : mk(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < HB_DU; ++u) {
+          const int r = r0 + u * c.ws;
+          if (r <= ihi) fma_acc_conj(s, a[u], sb[r - (k + 1)]);
+        }
       }
       s = warp_sum(s);
       if (c.lane == 0) st[l] = s;
@@ -132,9 +157,10 @@ SD_DEV void cta_hb_panel_step(const Cta& c, const HessBatch& hb, int mat, int pa
     for (int q = c.tid; q < nr; q += c.nt) {                // b -= V w
       const int r = k + 1 + q;
       cplx s = sb[q];
-      for (int l = 0; l < j; ++l) {
-        if (r <= k + l) break;
-        const cplx vr = (r == k + l + 1) ? mk(1.0, 0.0) : A[r + (size_t)(k + l) * lda];
+      const int lmax = (q + 1 < j) ? q + 1 : j;              // reflector l reaches rows r > k + l, i.e. l <= q
+#pragma unroll 4
+      for (int l = 0; l < lmax; ++l) {
+        const cplx vr = (l == q) ? mk(1.0, 0.0) : A[r + (size_t)(k + l) * lda];
         s -= vr * sw[l];
       }
       acol[r] = s;

@@ -225,8 +225,10 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
 // ---------------------------------------------------------------------------------------------
 SD_DEV Refl zero_refl() { Refl r; r.v2 = mk(0.0, 0.0); r.tau = mk(0.0, 0.0); return r; }
 
+template <int NSC>
 SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, int I,
-                        const cplx* shifts, int ns, int ta, int tb, Refl* rec, Refl* cur) {
+                        const cplx* shifts, int ns_rt, int ta, int tb, Refl* rec, Refl* cur) {
+  const int ns = NSC ? NSC : ns_rt;                          // compile-time shift count when known (index arithmetic by shifts)
   const int smax = I - 1 - L;
   const int kb0 = L - g0;                                   // local position of a bulge at s = 0
   const int ilast = I - g0;                                 // last local row / column of the active block
@@ -306,46 +308,48 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
       const int nR = khi;                                    // right-only rows 0 .. khi-1
       const int nq = (ns + 3) >> 2;
       const int nline = nL + nR;
-      const int njobs = ntile + nline * nq;
-      for (int j = g.tid - nbt; j < njobs; j += g.nt - nbt) {
-        if (j < ntile) {
-          const int p = j / ns, i = j - p * ns;
-          int b, bp;
-          if (i <= p) { b = p + 1; bp = i; } else { b = ns - 1 - p; bp = i - p - 1; }
-          if (bp < blo || b > bhi) continue;
-          const int kr = kb0 + t - 2 * b, kc = kb0 + t - 2 * bp;
-          cplx* q0 = S + kr + kc * lds;
-          cplx a00 = q0[0], a10 = q0[1], a01 = q0[lds], a11 = q0[lds + 1];
-          const Refl rl = cb[b], rr = cb[bp];
-          apply_left(rl, a00, a10); apply_left(rl, a01, a11);
-          apply_right(rr, a00, a01); apply_right(rr, a10, a11);
-          q0[0] = a00; q0[1] = a10; q0[lds] = a01; q0[lds + 1] = a11;
-        } else {
-          const int u = j - ntile;
-          const int q = u / nline, line = u - q * nline;     // consecutive threads: consecutive lines (bank-conflict free)
-          if (line < nL) {                                   // column c0 + line: left applications of bulges 4q .. 4q+3
-            cplx* col = S + (c0 + line) * lds;
+      const int w0 = g.tid - nbt, wn = g.nt - nbt;
+      for (int j = w0; j < ntile; j += wn) {
+        const int p = j / ns, i = j - p * ns;
+        int b, bp;
+        if (i <= p) { b = p + 1; bp = i; } else { b = ns - 1 - p; bp = i - p - 1; }
+        if (bp < blo || b > bhi) continue;
+        const int kr = kb0 + t - 2 * b, kc = kb0 + t - 2 * bp;
+        cplx* q0 = S + kr + kc * lds;
+        cplx a00 = q0[0], a10 = q0[1], a01 = q0[lds], a11 = q0[lds + 1];
+        const Refl rl = cb[b], rr = cb[bp];
+        apply_left(rl, a00, a10); apply_left(rl, a01, a11);
+        apply_right(rr, a00, a01); apply_right(rr, a10, a11);
+        q0[0] = a00; q0[1] = a10; q0[lds] = a01; q0[lds + 1] = a11;
+      }
+      // line jobs continue the job numbering after the tiles, so the threads without a tile take the first lines
+      const int nlj = nline * nq;
+      int jj = w0 - (ntile % wn); if (jj < 0) jj += wn;
+      for (int u = jj; u < nlj; u += wn) {
+        int q = 0, line = u;                                 // q = u / nline without a division (nq is small)
+        while (line >= nline) { line -= nline; ++q; }        // consecutive threads: consecutive lines (bank-conflict free)
+        if (line < nL) {                                     // column c0 + line: left applications of bulges 4q .. 4q+3
+          cplx* col = S + (c0 + line) * lds;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int b = 4 * q + e;
-              if (b >= blo && b <= bhi) {
-                const int k = kb0 + t - 2 * b;
-                cplx x1 = col[k], x2 = col[k + 1];
-                apply_left(cb[b], x1, x2);
-                col[k] = x1; col[k + 1] = x2;
-              }
+          for (int e = 0; e < 4; ++e) {
+            const int b = 4 * q + e;
+            if (b >= blo && b <= bhi) {
+              const int k = kb0 + t - 2 * b;
+              cplx x1 = col[k], x2 = col[k + 1];
+              apply_left(cb[b], x1, x2);
+              col[k] = x1; col[k + 1] = x2;
             }
-          } else {                                           // row (line - nL): right applications of bulges 4q .. 4q+3
-            cplx* row = S + (line - nL);
+          }
+        } else {                                             // row (line - nL): right applications of bulges 4q .. 4q+3
+          cplx* row = S + (line - nL);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int b = 4 * q + e;
-              if (b >= blo && b <= bhi) {
-                const int k = kb0 + t - 2 * b;
-                cplx x1 = row[k * lds], x2 = row[(k + 1) * lds];
-                apply_right(cb[b], x1, x2);
-                row[k * lds] = x1; row[(k + 1) * lds] = x2;
-              }
+          for (int e = 0; e < 4; ++e) {
+            const int b = 4 * q + e;
+            if (b >= blo && b <= bhi) {
+              const int k = kb0 + t - 2 * b;
+              cplx x1 = row[k * lds], x2 = row[(k + 1) * lds];
+              apply_right(cb[b], x1, x2);
+              row[k * lds] = x1; row[(k + 1) * lds] = x2;
             }
           }
         }
@@ -642,26 +646,30 @@ SD_DEV void slabs_stream(const Cta& c, cplx* H, int ldh, int L, int I, int g0, i
   const bool steady = (ta >= 2 * (NSB - 1)) && (tb - 1 <= smax);
 #ifndef STAB_EMU
   {
-    const int part = c.tid & 1, half = c.nt >> 1;
+    // work unit = 16 lines (one warp of lane pairs); the units of BOTH slabs are dealt round-robin to the
+    // warps, so a warp never idles through a whole round because the other slab's line count is ragged
+    const int part = c.tid & 1, lp = c.lane >> 1;
     const int nleft = I - g1, nright = g0 - L;              // left slab columns (g1, I], right slab rows [L, g0)
-    for (int base_i = 0; base_i < nleft; base_i += half) {
-      const int li = base_i + (c.tid >> 1);
-      const bool act = li < nleft;
-      const unsigned mask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        cplx* line = H + (size_t)(g1 + 1 + li) * ldh;
-        if (steady) slab_line_pair<NSB, false, true>(line, 1, L, smax, ta, tb, rec, mask, part);
-        else slab_line_pair<NSB, false, false>(line, 1, L, smax, ta, tb, rec, mask, part);
-      }
-    }
-    for (int base_i = 0; base_i < nright; base_i += half) {
-      const int li = base_i + (c.tid >> 1);
-      const bool act = li < nright;
-      const unsigned mask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        cplx* line = H + (L + li);
-        if (steady) slab_line_pair<NSB, true, true>(line, (size_t)ldh, L, smax, ta, tb, rec, mask, part);
-        else slab_line_pair<NSB, true, false>(line, (size_t)ldh, L, smax, ta, tb, rec, mask, part);
+    const int UL = (nleft + 15) >> 4, UR = (nright + 15) >> 4;
+    for (int u = c.wid; u < UL + UR; u += c.nw) {
+      if (u < UL) {
+        const int li = (u << 4) + lp;
+        const bool act = li < nleft;
+        const unsigned mask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+          cplx* line = H + (size_t)(g1 + 1 + li) * ldh;
+          if (steady) slab_line_pair<NSB, false, true>(line, 1, L, smax, ta, tb, rec, mask, part);
+          else slab_line_pair<NSB, false, false>(line, 1, L, smax, ta, tb, rec, mask, part);
+        }
+      } else {
+        const int li = ((u - UL) << 4) + lp;
+        const bool act = li < nright;
+        const unsigned mask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+          cplx* line = H + (L + li);
+          if (steady) slab_line_pair<NSB, true, true>(line, (size_t)ldh, L, smax, ta, tb, rec, mask, part);
+          else slab_line_pair<NSB, true, false>(line, (size_t)ldh, L, smax, ta, tb, rec, mask, part);
+        }
       }
     }
   }
@@ -707,7 +715,8 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
     }
     cta_sync();
     HQR_PROF(2);
-    chase_tiles(g, sh.win, ldw, g0, wsz, L, I, sh.shifts, ns, ta, tb, sh.rec, sh.cur);
+    if (ns == 16) chase_tiles<16>(g, sh.win, ldw, g0, wsz, L, I, sh.shifts, ns, ta, tb, sh.rec, sh.cur);
+    else chase_tiles<0>(g, sh.win, ldw, g0, wsz, L, I, sh.shifts, ns, ta, tb, sh.rec, sh.cur);
     HQR_PROF(3);
     for (int q = c.tid; q < wsz * wsz; q += c.nt) {
       const int col = q / wsz, row = q - col * wsz;

@@ -210,14 +210,15 @@ __global__ void k_hessenberg(cplx* A, size_t astride, int n, const int* ilohi, c
 }
 
 // ---- stage 3b': batched blocked Hessenberg (hess_blocked.cuh) -------------------------------------
-__global__ void __launch_bounds__(256) k_hb_panel_step(HessBatch hb, int panel, int j) {
+__global__ void __launch_bounds__(512) k_hb_panel_step(HessBatch hb, int panel, int j) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* red = reinterpret_cast<double*>(smem_raw);
   cplx* sb = reinterpret_cast<cplx*>(smem_raw + 160 * sizeof(double));
   cplx* sw = sb + hb.n;
   cplx* st = sw + HB_NB;
+  cplx* sc = st + HB_NB;
   Cta c = make_cta(red);
-  cta_hb_panel_step(c, hb, hb.mat0 + blockIdx.x, panel, j, red, sb, sw, st);
+  cta_hb_panel_step(c, hb, hb.mat0 + blockIdx.x, panel, j, red, sb, sw, st, sc);
 }
 
 __global__ void __launch_bounds__(HB_GEMV_ROWS) k_hb_gemv(HessBatch hb, int panel, int j) {

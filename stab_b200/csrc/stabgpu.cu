@@ -194,7 +194,8 @@ static int hmark(stabgpu_plan* pl, cudaStream_t s, int cls) {
 // phase 1: the column loop (panel steps + HBM-bound GEMVs), phase 2: the tensor-core block updates
 int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, int p, bool mma, int phase) {
   const int N = pl->N;
-  const size_t sm_step = 160 * sizeof(double) + ((size_t)N + 2 * HB_NB) * sizeof(cplx);
+  const size_t sm_step = 160 * sizeof(double) + ((size_t)N + 3 * HB_NB) * sizeof(cplx);
+  const int pst = g_tune.hess_threads;                      // threads of the panel-step CTA
   const size_t sm_gemv = (size_t)N * sizeof(cplx);
   const size_t sm64 = GemmCfg<64, 64>::smem_bytes, sm6432 = GemmCfg<64, 32>::smem_bytes, sm3264 = GemmCfg<32, 64>::smem_bytes;
   const int k0 = p * HB_NB;                                  // smallest possible panel start (ilo = 0)
@@ -204,12 +205,12 @@ int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, 
   if (phase == 1) {
     dim3 ggemv((rows_max + HB_GEMV_ROWS - 1) / HB_GEMV_ROWS, HB_CHUNKS, nmat);
     for (int j = 0; j < HB_NB; ++j) {
-      k_hb_panel_step<<<nmat, 256, sm_step, s>>>(hb, p, j);
+      k_hb_panel_step<<<nmat, pst, sm_step, s>>>(hb, p, j);
       if (hmark(pl, s, 0)) return 1;
       k_hb_gemv<<<ggemv, HB_GEMV_ROWS, sm_gemv, s>>>(hb, p, j);
       if (hmark(pl, s, 1)) return 1;
     }
-    k_hb_panel_step<<<nmat, 256, sm_step, s>>>(hb, p, HB_NB);
+    k_hb_panel_step<<<nmat, pst, sm_step, s>>>(hb, p, HB_NB);
     if (hmark(pl, s, 0)) return 1;
     CU(cudaGetLastError());
     pl->launches += 2 * HB_NB + 1;

@@ -186,17 +186,18 @@ extern "C" int emu_hess_blocked(cplx* A, int n, int ilo, int ihi, cplx* tau, cpl
   const int P = (n - 1 + HB_NB - 1) / HB_NB;
   std::vector<cplx> Y((size_t)n * HB_NB), T((size_t)P * HB_NB * HB_NB), Yp((size_t)n * HB_CHUNKS), W((size_t)n * HB_NB);
   std::vector<cplx> sb(n), sw(HB_NB), st(HB_NB), sv(n);
+  std::vector<cplx> scv(HB_NB);
   std::vector<double> smem(GemmCfg<64, 64>::smem_bytes / sizeof(double));
   int ilohi[2] = {ilo, ihi};
   HessBatch hb{A, (size_t)n * n, n, ilohi, tau, Y.data(), T.data(), Yp.data(), W.data(), P, 0};
   const int tiles = (n + 63) / 64;
   for (int p = 0; p < P; ++p) {
     for (int j = 0; j < HB_NB; ++j) {
-      cta_hb_panel_step(c, hb, 0, p, j, red.data(), sb.data(), sw.data(), st.data());
+      cta_hb_panel_step(c, hb, 0, p, j, red.data(), sb.data(), sw.data(), st.data(), scv.data());
       for (int rt = 0; rt * HB_GEMV_ROWS < n; ++rt)
         for (int ch = 0; ch < HB_CHUNKS; ++ch) cta_hb_gemv(c, hb, 0, p, j, rt, ch, sv.data());
     }
-    cta_hb_panel_step(c, hb, 0, p, HB_NB, red.data(), sb.data(), sw.data(), st.data());
+    cta_hb_panel_step(c, hb, 0, p, HB_NB, red.data(), sb.data(), sw.data(), st.data(), scv.data());
     for (int ti = 0; ti < tiles; ++ti) cta_hb_gemm<HB_YTOP, false>(c, hb, 0, p, ti, 0, smem.data());
     for (int r = 0; r < n; ++r) cta_hb_ytop_T(c, hb, 0, p, r);
     for (int ti = 0; ti < tiles; ++ti)
