@@ -81,9 +81,47 @@ SD_DEV void cta_gemm_tile(const Cta& c, double* smem, int i0, int j0, int m, int
   }
 #endif
   for (int k0 = 0; k0 < K; k0 += GEMM_KC) {
+#ifndef STAB_EMU
+    {
+      // all loads of both operand tiles are issued before the first shared-memory store (memory-level parallelism:
+      // the tile load is one DRAM round trip, not one per element)
+      constexpr int NLD = (TM * GEMM_KC) / GEMM_THREADS, NRD = (TN * GEMM_KC) / GEMM_THREADS;
+      cplx vl[NLD], vr[NRD];
+#pragma unroll
+      for (int u = 0; u < NLD; ++u) {
+        const int idx = c.tid + u * GEMM_THREADS;
+        int i, l;
+        // kfast operands: 4 consecutive k (64 B of memory) x 8 rows per warp -> full sectors AND conflict-free smem stores
+        if (LOp::kfast) { l = (idx & 3) + 4 * (idx / (4 * TM)); i = (idx >> 2) % TM; } else { i = idx % TM; l = idx / TM; }
+        vl[u] = mk(0.0, 0.0);
+        if (i0 + i < m && k0 + l < K) vl[u] = L(i0 + i, k0 + l);
+      }
+#pragma unroll
+      for (int u = 0; u < NRD; ++u) {
+        const int idx = c.tid + u * GEMM_THREADS;
+        int j, l;
+        if (ROp::kfast) { l = (idx & 3) + 4 * (idx / (4 * TN)); j = (idx >> 2) % TN; } else { j = idx % TN; l = idx / TN; }
+        vr[u] = mk(0.0, 0.0);
+        if (j0 + j < nc && k0 + l < K) vr[u] = R(k0 + l, j0 + j);
+      }
+#pragma unroll
+      for (int u = 0; u < NLD; ++u) {
+        const int idx = c.tid + u * GEMM_THREADS;
+        int i, l;
+        if (LOp::kfast) { l = (idx & 3) + 4 * (idx / (4 * TM)); i = (idx >> 2) % TM; } else { i = idx % TM; l = idx / TM; }
+        sL[l * G::SLD + 2 * i] = vl[u].re; sL[l * G::SLD + 2 * i + 1] = vl[u].im;
+      }
+#pragma unroll
+      for (int u = 0; u < NRD; ++u) {
+        const int idx = c.tid + u * GEMM_THREADS;
+        int j, l;
+        if (ROp::kfast) { l = (idx & 3) + 4 * (idx / (4 * TN)); j = (idx >> 2) % TN; } else { j = idx % TN; l = idx / TN; }
+        sR[l * G::SRD + 2 * j] = vr[u].re; sR[l * G::SRD + 2 * j + 1] = vr[u].im;
+      }
+    }
+#else
     for (int idx = c.tid; idx < TM * GEMM_KC; idx += c.nt) {
       int i, l;
-      // kfast operands: 4 consecutive k (64 B of memory) x 8 rows per warp -> full sectors AND conflict-free smem stores
       if (LOp::kfast) { l = (idx & 3) + 4 * (idx / (4 * TM)); i = (idx >> 2) % TM; } else { i = idx % TM; l = idx / TM; }
       cplx v = mk(0.0, 0.0);
       if (i0 + i < m && k0 + l < K) v = L(i0 + i, k0 + l);
@@ -96,6 +134,7 @@ SD_DEV void cta_gemm_tile(const Cta& c, double* smem, int i0, int j0, int m, int
       if (j0 + j < nc && k0 + l < K) v = R(k0 + l, j0 + j);
       sR[l * G::SRD + 2 * j] = v.re; sR[l * G::SRD + 2 * j + 1] = v.im;
     }
+#endif
     cta_sync();
     if (mma) {
 #ifndef STAB_EMU
