@@ -34,6 +34,7 @@ struct HessBatch {
   cplx* W;              // NB x n per matrix
   int P;
   int mat0;             // first matrix of this launch group (the batch is split over two streams)
+  cplx* Vx;             // n x NB per matrix: the current panel's V with explicit ones / zeros (pipelined GEMM path)
 };
 
 SD_DEV cplx hb_v(const cplx* A, int lda, int k, int ihi, int r, int l) {   // V(r, l) of the panel starting at k

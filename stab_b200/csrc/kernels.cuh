@@ -7,6 +7,7 @@
 #include "balance.cuh"
 #include "hessenberg.cuh"
 #include "hqr.cuh"
+#include "gemm_pipe.cuh"
 #include "evec.cuh"
 #include "lu.cuh"
 #include "hess_blocked.cuh"
@@ -233,6 +234,93 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_hb_gemm(HessBatch hb, int p
   Cta c = make_cta(nullptr);
   cta_hb_gemm<PHASE, USE_MMA>(c, hb, hb.mat0 + blockIdx.z, panel, blockIdx.x, blockIdx.y, reinterpret_cast<double*>(smem_raw));
 }
+
+#ifndef STAB_EMU
+// ---- pipelined DMMA GEMM path (gemm_pipe.cuh): plain operands, V materialised per panel ----------
+// Vx(r, l) = V(r, l) of the panel (zeros above / beyond the reflector, explicit one); grid (row blocks, batch)
+__global__ void k_hb_vx(HessBatch hb, int panel) {
+  const int mat = hb.mat0 + blockIdx.y, n = hb.n;
+  const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
+  const int k = ilo + panel * HB_NB;
+  if (k >= ihi) return;
+  const cplx* A = hb.A + (size_t)mat * hb.astride;
+  cplx* Vx = hb.Vx + (size_t)mat * n * HB_NB;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+#pragma unroll 8
+  for (int l = 0; l < HB_NB; ++l) Vx[r + (size_t)l * n] = hb_v(A, n, k, ihi, r, l);
+}
+
+enum PipePhase { PP_YTOP = 0, PP_RIGHT_TRAIL, PP_RIGHT_PANEL, PP_LEFT_W, PP_LEFT_UPD, PP_BT_W, PP_BT_UPD };
+
+template <int PHASE>
+struct HbProb {
+  HessBatch hb; cplx* X; size_t xstride; int panel;
+  SD_DEV GemmProb operator()(int matl) const {
+    GemmProb q;
+    const int mat = hb.mat0 + matl, n = hb.n, lda = n;
+    const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
+    const int k = ilo + panel * HB_NB;
+    q.m = 0; q.nc = 0; q.K = 0; q.L = nullptr; q.R = nullptr; q.C = nullptr; q.ldc = 1; q.lsi = q.lsl = q.rsl = q.rsj = 0;
+    if (k >= ihi) return q;
+    cplx* A = hb.A + (size_t)mat * hb.astride;
+    cplx* Y = hb.Y + (size_t)mat * n * HB_NB;
+    cplx* W = hb.W + (size_t)mat * n * HB_NB;
+    const cplx* Vx = hb.Vx + (size_t)mat * n * HB_NB;
+    if (PHASE == PP_YTOP) {                 // Y(0:k+1, :) = A(0:k+1, k+1:ihi+1) V(k+1:ihi+1, :)
+      q.m = k + 1; q.nc = HB_NB; q.K = ihi - k;
+      q.L = A + (size_t)(k + 1) * lda; q.lsi = 1; q.lsl = lda;
+      q.R = Vx + (k + 1); q.rsl = 1; q.rsj = n;
+      q.C = Y; q.ldc = n;
+    } else if (PHASE == PP_RIGHT_TRAIL) {   // A(0:ihi+1, k+NB:ihi+1) -= Y V(k+NB:ihi+1, :)^H
+      q.m = ihi + 1; q.nc = ihi + 1 - (k + HB_NB); q.K = HB_NB;
+      q.L = Y; q.lsi = 1; q.lsl = n;
+      q.R = Vx + (k + HB_NB); q.rsl = n; q.rsj = 1;
+      q.C = A + (size_t)(k + HB_NB) * lda; q.ldc = lda;
+    } else if (PHASE == PP_RIGHT_PANEL) {   // A(0:k+1, k+1:k+NB) -= Y(0:k+1, :) V(k+1:k+NB, :)^H
+      q.m = k + 1; q.nc = HB_NB - 1; if (q.nc > n - (k + 1)) q.nc = n - (k + 1); q.K = HB_NB;
+      q.L = Y; q.lsi = 1; q.lsl = n;
+      q.R = Vx + (k + 1); q.rsl = n; q.rsj = 1;
+      q.C = A + (size_t)(k + 1) * lda; q.ldc = lda;
+    } else if (PHASE == PP_LEFT_W) {        // W (NB x nc) = V^H A(k+1:ihi+1, k+NB:n)
+      q.m = HB_NB; q.nc = n - (k + HB_NB); q.K = ihi - k;
+      q.L = Vx + (k + 1); q.lsi = n; q.lsl = 1;
+      q.R = A + (k + 1) + (size_t)(k + HB_NB) * lda; q.rsl = 1; q.rsj = lda;
+      q.C = W; q.ldc = HB_NB;
+    } else if (PHASE == PP_LEFT_UPD) {      // A(k+1:ihi+1, k+NB:n) -= V W
+      q.m = ihi - k; q.nc = n - (k + HB_NB); q.K = HB_NB;
+      q.L = Vx + (k + 1); q.lsi = 1; q.lsl = n;
+      q.R = W; q.rsl = 1; q.rsj = HB_NB;
+      q.C = A + (k + 1) + (size_t)(k + HB_NB) * lda; q.ldc = lda;
+    } else if (PHASE == PP_BT_W) {          // W (NB x n) = V^H X(k+1:ihi+1, :)
+      cplx* Xm = X + (size_t)mat * xstride;
+      q.m = HB_NB; q.nc = n; q.K = ihi - k;
+      q.L = Vx + (k + 1); q.lsi = n; q.lsl = 1;
+      q.R = Xm + (k + 1); q.rsl = 1; q.rsj = n;
+      q.C = W; q.ldc = HB_NB;
+    } else {                                // X(k+1:ihi+1, :) -= V W
+      cplx* Xm = X + (size_t)mat * xstride;
+      q.m = ihi - k; q.nc = n; q.K = HB_NB;
+      q.L = Vx + (k + 1); q.lsi = 1; q.lsl = n;
+      q.R = W; q.rsl = 1; q.rsj = HB_NB;
+      q.C = Xm + (k + 1); q.ldc = n;
+    }
+    return q;
+  }
+};
+
+template <int PHASE>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_pipe(HessBatch hb, cplx* X, size_t xstride, int panel, int tiles_i, int tiles_j, int nmat) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  HbProb<PHASE> pf{hb, X, xstride, panel};
+  //                                    TM  TN  SUB    CONJL  CONJR  LKFAST RKFAST
+  if (PHASE == PP_YTOP)                                   gemm_pipe_run<64, 32, false, false, false, false, true>(pf, tiles_i, tiles_j, nmat, smem);
+  else if (PHASE == PP_RIGHT_TRAIL || PHASE == PP_RIGHT_PANEL) gemm_pipe_run<64, 32, true, false, true, false, false>(pf, tiles_i, tiles_j, nmat, smem);
+  else if (PHASE == PP_LEFT_W || PHASE == PP_BT_W)        gemm_pipe_run<32, 64, false, true, false, true, true>(pf, tiles_i, tiles_j, nmat, smem);
+  else                                                    gemm_pipe_run<64, 32, true, false, false, false, true>(pf, tiles_i, tiles_j, nmat, smem);
+}
+#endif
 
 __global__ void k_hb_ytop_T(HessBatch hb, int panel) {
   Cta c = make_cta(nullptr);

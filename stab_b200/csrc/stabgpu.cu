@@ -15,6 +15,7 @@ namespace {
 
 thread_local std::string g_err;
 int g_device = -1;
+int g_sm_count = 148;
 bool g_inited = false;
 struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int hess_streams = 1; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
@@ -44,6 +45,7 @@ int ensure_init() {
   }
   if (g_device >= ndev) return fail("libstabgpu: device index out of range");
   CU(cudaSetDevice(g_device));
+  { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, g_device) == cudaSuccess && pr.multiProcessorCount > 0) g_sm_count = pr.multiProcessorCount; }
   g_inited = true;
   return 0;
 }
@@ -100,7 +102,7 @@ struct stabgpu_plan {
   bool has_Re = false, has_Ma = false;
   // work
   DBuf<cplx> coef, A, C, Hq, V, tau, w, eig, lam;
-  DBuf<cplx> hbY, hbT, hbYp, hbW;      // blocked Hessenberg workspaces
+  DBuf<cplx> hbY, hbT, hbYp, hbW, hbVx;   // blocked Hessenberg workspaces (Vx: the panel's V with explicit ones / zeros)
   int hbP = 0;
   DBuf<double> scale, hnorm;
   DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr, vbad;
@@ -125,7 +127,7 @@ size_t per_point_bytes(int kind, int n, int N, int ny, int want_vectors) {
   if (want_vectors) b += 2 * (size_t)N * N * 16;     // Hq + V
   b += (size_t)ny * 150 * 16;                        // coefficients
   b += (size_t)N * (16 * 4 + 8 + 4 * 3) + 64;
-  b += (size_t)N * 16 * (3 * HB_NB + HB_CHUNKS) + 16 * HB_NB * HB_NB;   // blocked Hessenberg: Y, W, T, Ypart
+  b += (size_t)N * 16 * (4 * HB_NB + HB_CHUNKS) + 16 * HB_NB * HB_NB;   // blocked Hessenberg: Y, W, Vx, T, Ypart
   return b;
 }
 
@@ -151,7 +153,7 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
   if (pl->blkend.alloc((size_t)cap * N) || pl->kr.alloc((size_t)cap * N) || pl->vbad.alloc((size_t)cap * N)) return 1;
   pl->hbP = (N - 1 + HB_NB - 1) / HB_NB;
   if (pl->hbY.alloc((size_t)cap * N * HB_NB) || pl->hbT.alloc((size_t)cap * pl->hbP * HB_NB * HB_NB) ||
-      pl->hbYp.alloc((size_t)cap * N * HB_CHUNKS) || pl->hbW.alloc((size_t)cap * N * HB_NB)) return 1;
+      pl->hbYp.alloc((size_t)cap * N * HB_CHUNKS) || pl->hbW.alloc((size_t)cap * N * HB_NB) || pl->hbVx.alloc((size_t)cap * N * HB_NB)) return 1;
   if (pl->ilohi.alloc(2 * (size_t)cap) || pl->info_lu.alloc(cap) || pl->info_qr.alloc(cap) || pl->info_v.alloc(cap)) return 1;
   CU(cudaStreamCreate(&pl->stream));
   CU(cudaStreamCreate(&pl->stream2));
@@ -176,6 +178,27 @@ int launch_hb_gemm(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t
     CU(cudaFuncSetAttribute(k_hb_gemm<PHASE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_hb_gemm<PHASE, false><<<grid, GEMM_THREADS, smem, s>>>(hb, panel);
   }
+  CU(cudaGetLastError());
+  pl->launches += 1;
+  return 0;
+}
+
+
+// pipelined DMMA GEMM (gemm_pipe.cuh): persistent CTAs, two per SM
+template <int PHASE>
+int launch_pipe(stabgpu_plan* pl, const HessBatch& hb, cplx* X, size_t xstride, int nmat, cudaStream_t s, int panel, int ti, int tj) {
+  if (ti < 1 || tj < 1 || nmat < 1) return 0;
+  const size_t smem = (PHASE == PP_LEFT_W || PHASE == PP_BT_W) ? PipeCfg<32, 64>::smem_bytes : PipeCfg<64, 32>::smem_bytes;
+  CU(cudaFuncSetAttribute(k_gemm_pipe<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long total = (long long)ti * tj * nmat;
+  int grid = 2 * g_sm_count; if ((long long)grid > total) grid = (int)total;
+  k_gemm_pipe<PHASE><<<grid, GEMM_THREADS, smem, s>>>(hb, X, xstride, panel, ti, tj, nmat);
+  CU(cudaGetLastError());
+  pl->launches += 1;
+  return 0;
+}
+int launch_vx(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, int panel) {
+  k_hb_vx<<<dim3((hb.n + 127) / 128, nmat), 128, 0, s>>>(hb, panel);
   CU(cudaGetLastError());
   pl->launches += 1;
   return 0;
@@ -217,6 +240,23 @@ int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, 
     return 0;
   }
   const int tm = (N + 63) / 64;
+  if (g_tune.hess_mode == 1) {               // pipelined path: plain operands (V materialised), persistent cp.async ring
+    if (launch_vx(pl, hb, nmat, s, p)) return 1;
+    if (launch_pipe<PP_YTOP>(pl, hb, nullptr, 0, nmat, s, p, tm, 1)) return 1;
+    k_hb_ytop_T<<<dim3((N + 127) / 128, nmat), 128, 0, s>>>(hb, p);
+    pl->launches += 1;
+    if (trail_max > 0 && launch_pipe<PP_RIGHT_TRAIL>(pl, hb, nullptr, 0, nmat, s, p, tm, (trail_max + 31) / 32)) return 1;
+    if (launch_pipe<PP_RIGHT_PANEL>(pl, hb, nullptr, 0, nmat, s, p, tm, 1)) return 1;
+    if (trail_max > 0) {
+      if (launch_pipe<PP_LEFT_W>(pl, hb, nullptr, 0, nmat, s, p, 1, (trail_max + 63) / 64)) return 1;
+      k_hb_w_T<<<dim3((trail_max + 127) / 128, nmat), 128, 0, s>>>(hb, p);
+      pl->launches += 1;
+      if (launch_pipe<PP_LEFT_UPD>(pl, hb, nullptr, 0, nmat, s, p, (rows_max + 63) / 64, (trail_max + 31) / 32)) return 1;
+    }
+    if (hmark(pl, s, 2)) return 1;
+    CU(cudaGetLastError());
+    return 0;
+  }
   if (launch_hb_gemm<HB_YTOP>(pl, hb, nmat, s, p, tm, 1, sm6432, mma)) return 1;
   k_hb_ytop_T<<<dim3((N + 127) / 128, nmat), 128, 0, s>>>(hb, p);
   pl->launches += 1;
@@ -252,8 +292,8 @@ int run_hessenberg(stabgpu_plan* pl) {
     pl->launches += 1;
     return 0;
   }
-  const bool mma = g_tune.hess_mode == 1;
-  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0};
+  const bool mma = g_tune.hess_mode == 1 || g_tune.hess_mode == 3;   // 1: pipelined DMMA kernels, 3: the tile-per-CTA DMMA kernels
+  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p};
   pl->pev_n = 0;
   if (hmark(pl, s, 3)) return 1;
   const int half = (g_tune.hess_streams >= 2 && np >= 16) ? (np + 1) / 2 : np;
@@ -341,11 +381,19 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
                                               0, pl->V.p, st, pl->info_v.p, pl->vbad.p, 1);
   CU(cudaGetLastError());
   pl->launches += 1;
-  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0};
+  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p};
   const int tn = (N + 63) / 64;
   for (int p = pl->hbP - 1; p >= 0; --p) {
     const int rows_max = N - 1 - p * HB_NB;
     if (rows_max <= 0) continue;
+    if (g_tune.hess_mode == 1) {
+      if (launch_vx(pl, hb, np, s, p)) return 1;
+      if (launch_pipe<PP_BT_W>(pl, hb, pl->V.p, st, np, s, p, 1, tn)) return 1;
+      k_bt_w_T<<<dim3((N + 127) / 128, np), 128, 0, s>>>(hb, p);
+      pl->launches += 1;
+      if (launch_pipe<PP_BT_UPD>(pl, hb, pl->V.p, st, np, s, p, (rows_max + 63) / 64, (N + 31) / 32)) return 1;
+      continue;
+    }
     if (launch_bt_gemm<BT_W>(pl, hb, p, 1, tn, GemmCfg<32, 64>::smem_bytes)) return 1;
     k_bt_w_T<<<dim3((N + 127) / 128, np), 128, 0, s>>>(hb, p);
     pl->launches += 1;
