@@ -272,6 +272,7 @@ def main():
     plan.profile_hessenberg(True)
     plan.execute()
     hess_bd = plan.profile_hessenberg(False)
+    evec_bd = plan.profile_eigvec() if want_vectors else {}
     ilohi = plan.ilohi()
     plan_info = np.zeros(P, dtype=np.int32)
     sb.lib().stabgpu_plan_download(plan._h, None, None, plan_info.ctypes.data)
@@ -340,7 +341,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
         pass
-    roofline = {"kernel": "Hessenberg stage (k_hb_panel_step + k_hb_gemv + k_hb_gemm<*>): the graded stage of the north star",
+    roofline = {"kernel": "Hessenberg stage (k_hb_panel_step + k_hb_gemv + k_gemm_pipe<*>): the graded stage of the north star",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "traffic": None, "flops_per_step": hess_flops,
                 "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 burst via torch.matmul (MEASURED_PEAKS.json has no FP64 entry)",
@@ -353,8 +354,9 @@ def main():
                      "algorithmic_bytes_per_step": gemv_bytes, "ms_per_step": gemv_ms, "launches_per_step": 32 * int(np.ceil((n - 1) / 32)),
                      "peak_source": hbm_src,
                      "traffic": (traffic or {}).get("k_hb_gemv"), "timing": "CUDA events after every kernel, separate profiled execute"}
-    roofline_gemm = {"kernel": "k_hb_gemm<*> (DMMA rank-32 updates)", "bound": "tensor", "achieved": gemm_tf, "peak": peak,
-                     "unit": "TFLOP/s", "frac": gemm_tf / peak if peak else None, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms}
+    roofline_gemm = {"kernel": "k_gemm_pipe<*> (persistent cp.async-pipelined DMMA GEMM: rank-32 updates and V^H A products of the Hessenberg stage)", "bound": "tensor", "achieved": gemm_tf, "peak": peak,
+                     "unit": "TFLOP/s", "frac": gemm_tf / peak if peak else None, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
+                     "traffic": (traffic or {}).get("k_gemm_pipe")}
     asm_ms = stage_ms.get("assemble", 0.0)
     asm_gbs = 16.0 * n * n * P / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0
     dominant = max(stage_ms, key=stage_ms.get)
@@ -374,6 +376,7 @@ def main():
         "stages_ms_per_step": stage_ms,
         "dominant_stage": (dominant + " (shifted QR: latency / FP64-vector bound, no clean roofline -- time share only, SURVEY 8d)") if dominant == "qr" else dominant,
         "hessenberg_breakdown_ms": hess_bd,
+        "eigvec_breakdown_ms": evec_bd,
         "assembly_roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": asm_gbs / hbm_peak if hbm_peak else None},
         "failed_points": n_fail,

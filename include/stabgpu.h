@@ -137,7 +137,8 @@ long long stabgpu_plan_launch_count(stabgpu_plan* plan);
  * the time per kernel class of the last profiled execute: panel step, GEMV (HBM bound), tensor-core block updates, other */
 /* (ilo, ihi) of ZGEBAL per point of the last execute, 0-based inclusive: 2*npts ints (sizes the algorithmic work) */
 int stabgpu_plan_ilohi(stabgpu_plan* plan, int* ilohi);
-int stabgpu_plan_profile_hessenberg(stabgpu_plan* plan, int enable, float* ms4);                         /* kernels launched by the last execute */
+int stabgpu_plan_profile_hessenberg(stabgpu_plan* plan, int enable, float* ms4);
+int stabgpu_plan_profile_eigvec(stabgpu_plan* plan, float* ms3);   /* inverse iteration, back-transformation GEMMs, finalize (same profiled execute) */                         /* kernels launched by the last execute */
 void* stabgpu_plan_stream(stabgpu_plan* plan);                                   /* the cudaStream_t the plan launches on (for external CUDA-event timing) */
 void* stabgpu_plan_eig_dev(stabgpu_plan* plan);                                  /* DEVICE pointer: sorted eigenvalues, N x npts complex (for the multi-GPU result gather) */
 int stabgpu_plan_capacity(stabgpu_plan* plan);                                   /* points per wave that fit the device workspace */

@@ -101,6 +101,7 @@ def lib():
     proto("stabgpu_plan_stream", vp, [vp])
     proto("stabgpu_plan_ilohi", i, [vp, vp])
     proto("stabgpu_plan_profile_hessenberg", i, [vp, i, C.POINTER(C.c_float)])
+    proto("stabgpu_plan_profile_eigvec", i, [vp, C.POINTER(C.c_float)])
     proto("stabgpu_plan_capacity", i, [vp])
     proto("stabgpu_plan_eig_dev", vp, [vp])
     proto("stabgpu_plan_destroy", i, [vp])
@@ -425,6 +426,12 @@ class Plan:
         ms = (C.c_float * 4)()
         lib().stabgpu_plan_profile_hessenberg(self._h, 1 if enable else 0, ms)
         return dict(zip(("panel_step", "gemv", "gemm", "other"), (float(v) for v in ms)))
+
+    def profile_eigvec(self) -> dict:
+        """Per-kernel-class times of the eigenvector stage from the last profiled execute."""
+        ms = (C.c_float * 3)()
+        lib().stabgpu_plan_profile_eigvec(self._h, ms)
+        return dict(zip(("invit", "bt_gemm", "finalize"), (float(v) for v in ms)))
 
     def launch_count(self) -> int:
         return int(lib().stabgpu_plan_launch_count(self._h))

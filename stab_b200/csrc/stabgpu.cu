@@ -92,7 +92,7 @@ struct stabgpu_plan {
   std::vector<cudaEvent_t> evA, evB;
   bool prof_hess = false;                 // record events around every Hessenberg kernel class (bench breakdown)
   std::vector<cudaEvent_t> pev; size_t pev_n = 0; std::vector<int> pev_cls;
-  float hess_ms[4] = {0, 0, 0, 0};        // panel_step, gemv, gemm, other
+  float hess_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // panel_step, gemv, gemm, other, invit, back-transformation GEMM, finalize, -
   // grid / profile
   DBuf<double> vm, g2, g22, deta, d2eta, D1, D2, Dt2w, h5;
   bool has_h5 = false;
@@ -370,6 +370,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
   }
   const int rounds = 4;
   int rc;
+  if (hmark(pl, s, 7)) return 1;               // start marker of the eigenvector breakdown (class 7: not reported)
   if (N <= 128) rc = launch_invit<4>(pl, rounds);
   else if (N <= 256) rc = launch_invit<8>(pl, rounds);
   else if (N <= 384) rc = launch_invit<12>(pl, rounds);
@@ -381,6 +382,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
                                               0, pl->V.p, st, pl->info_v.p, pl->vbad.p, 1);
   CU(cudaGetLastError());
   pl->launches += 1;
+  if (hmark(pl, s, 4)) return 1;
   HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p};
   const int tn = (N + 63) / 64;
   for (int p = pl->hbP - 1; p >= 0; --p) {
@@ -399,6 +401,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
     pl->launches += 1;
     if (launch_bt_gemm<BT_UPD>(pl, hb, p, (rows_max + 63) / 64, tn, GemmCfg<64, 64>::smem_bytes)) return 1;
   }
+  if (hmark(pl, s, 5)) return 1;
   {
     const size_t smf = 8 * (size_t)N * sizeof(cplx);
     CU(cudaFuncSetAttribute(k_vec_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
@@ -407,6 +410,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
     k_vec_finalize<<<dim3(ch, np), 256, smf, s>>>(pl->V.p, st, N, pl->ilohi.p, pl->scale.p, scale_rows);
     CU(cudaGetLastError());
     pl->launches += 1;
+    if (hmark(pl, s, 6)) return 1;
   }
   return 0;
 }
@@ -607,11 +611,11 @@ int stabgpu_plan_execute(stabgpu_plan* pl) {
   }
   CU(cudaStreamSynchronize(s));
   if (pl->prof_hess && pl->pev_n > 1) {
-    for (int c = 0; c < 4; ++c) pl->hess_ms[c] = 0.f;
+    for (int c = 0; c < 8; ++c) pl->hess_ms[c] = 0.f;
     for (size_t i = 1; i < pl->pev_n; ++i) {
       float t = 0.f;
       cudaEventElapsedTime(&t, pl->pev[i - 1], pl->pev[i]);
-      pl->hess_ms[pl->pev_cls[i] < 3 ? pl->pev_cls[i] : 3] += t;
+      pl->hess_ms[pl->pev_cls[i] < 8 ? pl->pev_cls[i] : 3] += t;
     }
   }
   for (int i = 0; i < ST_N; ++i) {
@@ -651,6 +655,12 @@ void* stabgpu_plan_stream(stabgpu_plan* pl) { return pl ? (void*)pl->stream : nu
 int stabgpu_plan_capacity(stabgpu_plan* pl) { return pl ? pl->cap : 0; }
 
 /* per-kernel-class breakdown of the Hessenberg stage: enable, execute once, read ms[4] = panel_step, gemv, gemm, other */
+int stabgpu_plan_profile_eigvec(stabgpu_plan* pl, float* ms3) {
+  if (!pl) return 1;
+  if (ms3) for (int c = 0; c < 3; ++c) ms3[c] = pl->hess_ms[4 + c];
+  return 0;
+}
+
 int stabgpu_plan_profile_hessenberg(stabgpu_plan* pl, int enable, float* ms4) {
   if (!pl) return 1;
   pl->prof_hess = enable != 0;
