@@ -131,7 +131,7 @@ struct InvitSlot<NS, -1> {
   SD_DEV static void run(int, int, bool, int, const cplx*, cplx*, cplx, double, cplx (&)[NS], cplx (&)[NS], unsigned&, cplx&, cplx&, int&, Prefetch&) {}
 };
 
-// grid: (ceil(n / (8*rounds)), batch), block 256.  smem: 2 * INVIT_CB * n complex.  n <= 32 NS.
+// grid: (ceil(n / (8*rounds)), batch), block 256.  smem: 2 * INVIT_CB * n complex + INVIT_WARPS * n bytes.  n <= 32 NS.
 template <int NS>
 __global__ void __launch_bounds__(INVIT_WARPS * 32, 1)
 k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restrict__ lam, const int* __restrict__ kr,
@@ -186,34 +186,50 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
     int buf = 0;
     prefetch((n - 1) >> 3, 0);
     InvitSlot<NS, NS - 1>::run(n, m, live, lane, H, sH, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
-    // ---- k = 0, then x = T_{m-1} ... T_1 y (forward recurrence carried by shuffles) ----
+    // ---- k = 0, then x = T_{m-1} ... T_1 y: a first-order recurrence in k.  The warp parks y, the multipliers and
+    // the interchange flags in the (now idle) staging buffers and ONE lane runs the recurrence from shared memory
+    // (~25 dependent cycles per row) instead of three warp shuffles per row ----
+    __syncthreads();                                        // every warp has finished reading the staged columns
     int isbad = 0;
     if (live) {
-      cplx piv = cdiag;
-      if (is_zero(piv)) piv = mk(eps3, 0.0);
-      cplx prev = cdiv(ydiag, piv);                         // current value of y[k-1]
+      cplx* wy = sH + (size_t)wid * 2 * n;
+      cplx* wc = wy + n;
+      unsigned char* wf = reinterpret_cast<unsigned char*>(sH + (size_t)2 * INVIT_CB * n) + (size_t)wid * n;
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        if (32 * s < m) {
-          const unsigned fl_s = flags;                      // each lane's own flag word
-          for (int i = (s == 0 ? 1 : 0); i < 32 && 32 * s + i < m; ++i) {
-            const cplx yk_in = shfl_c(y[s], i);
-            const cplx mk_ = shfl_c(c[s], i);
-            const unsigned fl = __shfl_sync(0xffffffffu, fl_s, i);
-            const cplx t = yk_in - mk_ * prev;
-            const bool f = (fl >> s) & 1u;
-            const cplx fin = f ? t : prev;                  // final x[k-1]
-            prev = f ? prev : t;
-            if (i > 0) { if (lane == i - 1) y[s] = fin; }
-            else { if (lane == 31) y[s > 0 ? s - 1 : 0] = fin; }
-          }
-        }
+        const int r = 32 * s + lane;
+        if (r < m) { wy[r] = y[s]; wc[r] = c[s]; wf[r] = (unsigned char)((flags >> s) & 1u); }
       }
-      {
-        const int rl = m - 1;                               // last row gets the carried value
+      __syncwarp();
+      if (lane == 0) {
+        cplx piv = cdiag;
+        if (is_zero(piv)) piv = mk(eps3, 0.0);
+        cplx prev = cdiv(ydiag, piv);                       // current value of y[k-1]
+        int k = 1;
+        for (; k + 3 < m; k += 4) {                         // loads of four rows in flight, recurrence in order
+          const cplx y0 = wy[k], y1 = wy[k + 1], y2 = wy[k + 2], y3 = wy[k + 3];
+          const cplx m0 = wc[k], m1 = wc[k + 1], m2 = wc[k + 2], m3 = wc[k + 3];
+          const bool f0 = wf[k] != 0, f1 = wf[k + 1] != 0, f2 = wf[k + 2] != 0, f3 = wf[k + 3] != 0;
+          cplx t, fin;
+          t = y0 - m0 * prev; fin = f0 ? t : prev; prev = f0 ? prev : t; wy[k - 1] = fin;
+          t = y1 - m1 * prev; fin = f1 ? t : prev; prev = f1 ? prev : t; wy[k] = fin;
+          t = y2 - m2 * prev; fin = f2 ? t : prev; prev = f2 ? prev : t; wy[k + 1] = fin;
+          t = y3 - m3 * prev; fin = f3 ? t : prev; prev = f3 ? prev : t; wy[k + 2] = fin;
+        }
+        for (; k < m; ++k) {
+          const cplx t = wy[k] - wc[k] * prev;
+          const bool f = wf[k] != 0;
+          const cplx fin = f ? t : prev;                    // final x[k-1]
+          prev = f ? prev : t;
+          wy[k - 1] = fin;
+        }
+        wy[m - 1] = prev;                                   // last row gets the carried value
+      }
+      __syncwarp();
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
-          if (32 * s + lane == rl) y[s] = prev;
+      for (int s = 0; s < NS; ++s) {
+        const int r = 32 * s + lane;
+        if (r < m) y[s] = wy[r];
       }
       double vn = 0.0;
 #pragma unroll

@@ -334,7 +334,7 @@ template <int NS>
 int launch_invit(stabgpu_plan* pl, int rounds) {
   const int N = pl->N, np = pl->npts;
   const size_t st = (size_t)N * N;
-  const size_t sm = 2 * (size_t)INVIT_CB * N * sizeof(cplx);
+  const size_t sm = 2 * (size_t)INVIT_CB * N * sizeof(cplx) + (size_t)INVIT_WARPS * N;
   CU(cudaFuncSetAttribute(k_invit<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   dim3 grid((N + INVIT_WARPS * rounds - 1) / (INVIT_WARPS * rounds), np);
   k_invit<NS><<<grid, INVIT_WARPS * 32, sm, pl->stream>>>(pl->A.p, st, N, pl->lam.p, pl->kr.p, pl->hnorm.p, pl->V.p, st, pl->vbad.p, rounds);
