@@ -101,7 +101,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    sample = args.cpu_sample or min(args.points, max(4 * cores, 32))
+    sample = args.cpu_sample or min(args.points, max(8 * cores, 64))
     alphas = np.linspace(0.05, 0.45, sample, endpoint=False)
     want_vectors = not args.no_vectors
     times = []
@@ -383,7 +383,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
-        sample = args.cpu_sample or min(P, max(4 * cores, 32))
+        sample = args.cpu_sample or min(P, max(16 * cores, 64))     # ~10-15 s of CPU work on the box's host cores
         rate, used, dt, as_coded = cpu_arm(ny, np.linspace(0.05, 0.45, sample, endpoint=False), want_vectors)
         line["cpu_baseline"] = {"value": rate, "unit": "eigensolves/s", "cores": used, "kind": "port",
                                 "sample": f"{sample} points of the same sweep, one worker per core, 1 BLAS thread each, "

@@ -89,6 +89,8 @@ struct stabgpu_plan {
   int want_vectors = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  cudaEvent_t evSub[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* evec_host = nullptr;            // when set (batch C-ABI calls): eigenvectors are copied to the host per sub-batch, overlapped
   std::vector<cudaEvent_t> evA, evB;
   bool prof_hess = false;                 // record events around every Hessenberg kernel class (bench breakdown)
   std::vector<cudaEvent_t> pev; size_t pev_n = 0; std::vector<int> pev_cls;
@@ -321,8 +323,8 @@ int run_hessenberg(stabgpu_plan* pl) {
 }
 
 template <int PHASE>
-int launch_bt_gemm(stabgpu_plan* pl, const HessBatch& hb, int panel, int ti, int tj, size_t smem) {
-  dim3 grid(ti, tj, pl->npts);
+int launch_bt_gemm(stabgpu_plan* pl, const HessBatch& hb, int nmat, int panel, int ti, int tj, size_t smem) {
+  dim3 grid(ti, tj, nmat);
   CU(cudaFuncSetAttribute(k_bt_gemm<PHASE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_bt_gemm<PHASE, true><<<grid, GEMM_THREADS, smem, pl->stream>>>(hb, pl->V.p, (size_t)pl->N * pl->N, panel);
   CU(cudaGetLastError());
@@ -331,13 +333,14 @@ int launch_bt_gemm(stabgpu_plan* pl, const HessBatch& hb, int panel, int ti, int
 }
 
 template <int NS>
-int launch_invit(stabgpu_plan* pl, int rounds) {
-  const int N = pl->N, np = pl->npts;
+int launch_invit(stabgpu_plan* pl, int rounds, int m0, int cnt) {
+  const int N = pl->N;
   const size_t st = (size_t)N * N;
   const size_t sm = 2 * (size_t)INVIT_CB * N * sizeof(cplx) + (size_t)INVIT_WARPS * N;
   CU(cudaFuncSetAttribute(k_invit<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  dim3 grid((N + INVIT_WARPS * rounds - 1) / (INVIT_WARPS * rounds), np);
-  k_invit<NS><<<grid, INVIT_WARPS * 32, sm, pl->stream>>>(pl->A.p, st, N, pl->lam.p, pl->kr.p, pl->hnorm.p, pl->V.p, st, pl->vbad.p, rounds);
+  dim3 grid((N + INVIT_WARPS * rounds - 1) / (INVIT_WARPS * rounds), cnt);
+  k_invit<NS><<<grid, INVIT_WARPS * 32, sm, pl->stream>>>(pl->A.p + (size_t)m0 * st, st, N, pl->lam.p + (size_t)m0 * N, pl->kr.p + (size_t)m0 * N,
+                                                          pl->hnorm.p + m0, pl->V.p + (size_t)m0 * st, st, pl->vbad.p + (size_t)m0 * N, rounds);
   CU(cudaGetLastError());
   pl->launches += 1;
   return 0;
@@ -345,6 +348,8 @@ int launch_invit(stabgpu_plan* pl, int rounds) {
 
 // Stage 6: right eigenvectors.  evec_mode 1 (default, N <= 640 and blocked Hessenberg factors available):
 // register-resident inverse iteration -> GEMM back-transformation -> finalize; otherwise the v1 warp kernel.
+// The batch is processed in sub-batches; when the caller registered a host destination (the batch C-ABI calls), the
+// finished vectors of sub-batch i travel to the host on the copy stream while sub-batch i+1 is computed.
 int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
   const int N = pl->N, np = pl->npts;
   const size_t st = (size_t)N * N;
@@ -356,61 +361,80 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
   const size_t sm_old = warps * per_warp;
   if (sm_old > 227 * 1024) return fail("libstabgpu: matrix too large for the eigenvector kernel");
   CU(cudaFuncSetAttribute(k_evec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_old));
-  int chunks = 1;
-  while (chunks * np < 2 * 148 && chunks * warps < N) chunks *= 2;
-  dim3 grid_old(chunks, np);
   const bool fast = g_tune.evec_mode == 1 && g_tune.hess_mode != 0 && N <= 640;
-  if (!fast) {
-    // the reflectors live in A (ZGEHRD layout); the QR ran on the copy Hq
-    k_evec<<<grid_old, warps * 32, sm_old, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->scale.p, pl->lam.p, pl->kr.p, pl->hnorm.p,
-                                                scale_rows, pl->V.p, st, pl->info_v.p, nullptr, 0);
-    CU(cudaGetLastError());
-    pl->launches += 1;
-    return 0;
-  }
-  const int rounds = 4;
-  int rc;
+  const int nsub = !pl->evec_host ? 1 : (np >= 8 * 37 ? 8 : (np >= 4 * 37 ? 4 : (np >= 2 ? 2 : 1)));   // >= 37 matrices per sub-batch keep the kernels full
   if (hmark(pl, s, 7)) return 1;               // start marker of the eigenvector breakdown (class 7: not reported)
-  if (N <= 128) rc = launch_invit<4>(pl, rounds);
-  else if (N <= 256) rc = launch_invit<8>(pl, rounds);
-  else if (N <= 384) rc = launch_invit<12>(pl, rounds);
-  else if (N <= 512) rc = launch_invit<16>(pl, rounds);
-  else rc = launch_invit<20>(pl, rounds);
-  if (rc) return 1;
-  // vectors the fast kernel rejected (no growth / overflow): ZLAEIN's retry vectors, v1 kernel, Hessenberg basis
-  k_evec<<<grid_old, warps * 32, sm_old, s>>>(pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->scale.p, pl->lam.p, pl->kr.p, pl->hnorm.p,
-                                              0, pl->V.p, st, pl->info_v.p, pl->vbad.p, 1);
-  CU(cudaGetLastError());
-  pl->launches += 1;
-  if (hmark(pl, s, 4)) return 1;
-  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p};
-  const int tn = (N + 63) / 64;
-  for (int p = pl->hbP - 1; p >= 0; --p) {
-    const int rows_max = N - 1 - p * HB_NB;
-    if (rows_max <= 0) continue;
-    if (g_tune.hess_mode == 1) {
-      if (launch_vx(pl, hb, np, s, p)) return 1;
-      if (launch_pipe<PP_BT_W>(pl, hb, pl->V.p, st, np, s, p, 1, tn)) return 1;
-      k_bt_w_T<<<dim3((N + 127) / 128, np), 128, 0, s>>>(hb, p);
+  for (int sb = 0; sb < nsub; ++sb) {
+    const int m0 = (int)((long long)np * sb / nsub), m1 = (int)((long long)np * (sb + 1) / nsub), cnt = m1 - m0;
+    if (cnt <= 0) continue;
+    int chunks = 1;
+    while (chunks * cnt < 2 * 148 && chunks * warps < N) chunks *= 2;
+    dim3 grid_old(chunks, cnt);
+    if (!fast) {
+      // the reflectors live in A (ZGEHRD layout); the QR ran on the copy Hq
+      k_evec<<<grid_old, warps * 32, sm_old, s>>>(pl->A.p + (size_t)m0 * st, st, N, pl->ilohi.p + 2 * m0, pl->tau.p + (size_t)m0 * N,
+                                                  pl->scale.p + (size_t)m0 * N, pl->lam.p + (size_t)m0 * N, pl->kr.p + (size_t)m0 * N,
+                                                  pl->hnorm.p + m0, scale_rows, pl->V.p + (size_t)m0 * st, st, pl->info_v.p + m0, nullptr, 0);
+      CU(cudaGetLastError());
       pl->launches += 1;
-      if (launch_pipe<PP_BT_UPD>(pl, hb, pl->V.p, st, np, s, p, (rows_max + 63) / 64, (N + 31) / 32)) return 1;
-      continue;
+    } else {
+      const int rounds = 4;
+      int rc;
+      if (N <= 128) rc = launch_invit<4>(pl, rounds, m0, cnt);
+      else if (N <= 256) rc = launch_invit<8>(pl, rounds, m0, cnt);
+      else if (N <= 384) rc = launch_invit<12>(pl, rounds, m0, cnt);
+      else if (N <= 512) rc = launch_invit<16>(pl, rounds, m0, cnt);
+      else rc = launch_invit<20>(pl, rounds, m0, cnt);
+      if (rc) return 1;
+      // vectors the fast kernel rejected (no growth / overflow): ZLAEIN's retry vectors, v1 kernel, Hessenberg basis
+      k_evec<<<grid_old, warps * 32, sm_old, s>>>(pl->A.p + (size_t)m0 * st, st, N, pl->ilohi.p + 2 * m0, pl->tau.p + (size_t)m0 * N,
+                                                  pl->scale.p + (size_t)m0 * N, pl->lam.p + (size_t)m0 * N, pl->kr.p + (size_t)m0 * N,
+                                                  pl->hnorm.p + m0, 0, pl->V.p + (size_t)m0 * st, st, pl->info_v.p + m0,
+                                                  pl->vbad.p + (size_t)m0 * N, 1);
+      CU(cudaGetLastError());
+      pl->launches += 1;
+      if (hmark(pl, s, 4)) return 1;
+      HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, m0, pl->hbVx.p};
+      const int tn = (N + 63) / 64;
+      for (int p = pl->hbP - 1; p >= 0; --p) {
+        const int rows_max = N - 1 - p * HB_NB;
+        if (rows_max <= 0) continue;
+        if (g_tune.hess_mode == 1) {
+          if (launch_vx(pl, hb, cnt, s, p)) return 1;
+          if (launch_pipe<PP_BT_W>(pl, hb, pl->V.p, st, cnt, s, p, 1, tn)) return 1;
+          k_bt_w_T<<<dim3((N + 127) / 128, cnt), 128, 0, s>>>(hb, p);
+          pl->launches += 1;
+          if (launch_pipe<PP_BT_UPD>(pl, hb, pl->V.p, st, cnt, s, p, (rows_max + 63) / 64, (N + 31) / 32)) return 1;
+          continue;
+        }
+        if (launch_bt_gemm<BT_W>(pl, hb, cnt, p, 1, tn, GemmCfg<32, 64>::smem_bytes)) return 1;
+        k_bt_w_T<<<dim3((N + 127) / 128, cnt), 128, 0, s>>>(hb, p);
+        pl->launches += 1;
+        if (launch_bt_gemm<BT_UPD>(pl, hb, cnt, p, (rows_max + 63) / 64, tn, GemmCfg<64, 64>::smem_bytes)) return 1;
+      }
+      if (hmark(pl, s, 5)) return 1;
+      {
+        const size_t smf = 8 * (size_t)N * sizeof(cplx);
+        CU(cudaFuncSetAttribute(k_vec_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+        int ch = 1;
+        while (ch * cnt < 4 * 148 && ch * 8 < N) ch *= 2;
+        k_vec_finalize<<<dim3(ch, cnt), 256, smf, s>>>(pl->V.p + (size_t)m0 * st, st, N, pl->ilohi.p + 2 * m0, pl->scale.p + (size_t)m0 * N, scale_rows);
+        CU(cudaGetLastError());
+        pl->launches += 1;
+        if (hmark(pl, s, 6)) return 1;
+      }
     }
-    if (launch_bt_gemm<BT_W>(pl, hb, p, 1, tn, GemmCfg<32, 64>::smem_bytes)) return 1;
-    k_bt_w_T<<<dim3((N + 127) / 128, np), 128, 0, s>>>(hb, p);
-    pl->launches += 1;
-    if (launch_bt_gemm<BT_UPD>(pl, hb, p, (rows_max + 63) / 64, tn, GemmCfg<64, 64>::smem_bytes)) return 1;
+    if (pl->evec_host) {                       // D2H of this sub-batch overlaps the next one
+      if (!pl->evSub[sb]) CU(cudaEventCreateWithFlags(&pl->evSub[sb], cudaEventDisableTiming));
+      CU(cudaEventRecord(pl->evSub[sb], s));
+      CU(cudaStreamWaitEvent(pl->stream2, pl->evSub[sb], 0));
+      CU(cudaMemcpyAsync(pl->evec_host + 2 * (size_t)m0 * st, pl->V.p + (size_t)m0 * st, sizeof(cplx) * (size_t)cnt * st,
+                         cudaMemcpyDeviceToHost, pl->stream2));
+    }
   }
-  if (hmark(pl, s, 5)) return 1;
-  {
-    const size_t smf = 8 * (size_t)N * sizeof(cplx);
-    CU(cudaFuncSetAttribute(k_vec_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
-    int ch = 1;
-    while (ch * np < 4 * 148 && ch * 8 < N) ch *= 2;
-    k_vec_finalize<<<dim3(ch, np), 256, smf, s>>>(pl->V.p, st, N, pl->ilohi.p, pl->scale.p, scale_rows);
-    CU(cudaGetLastError());
-    pl->launches += 1;
-    if (hmark(pl, s, 6)) return 1;
+  if (pl->evec_host) {                         // the compute stream's completion covers the copies as well
+    CU(cudaEventRecord(pl->evJoin, pl->stream2));
+    CU(cudaStreamWaitEvent(s, pl->evJoin, 0));
   }
   return 0;
 }
@@ -683,6 +707,7 @@ int stabgpu_plan_destroy(stabgpu_plan* pl) {
   if (pl->stream2) cudaStreamDestroy(pl->stream2);
   if (pl->evFork) cudaEventDestroy(pl->evFork);
   if (pl->evJoin) cudaEventDestroy(pl->evJoin);
+  for (int i = 0; i < 8; ++i) if (pl->evSub[i]) cudaEventDestroy(pl->evSub[i]);
   for (auto e : pl->evA) cudaEventDestroy(e);
   for (auto e : pl->evB) cudaEventDestroy(e);
   for (auto e : pl->pev) cudaEventDestroy(e);
@@ -719,9 +744,10 @@ static int batch_common(int kind, const stabgpu_params* p, const double* vm, con
   for (int p0 = 0; p0 < npts && !rc; p0 += pl->cap) {
     int m = npts - p0; if (m > pl->cap) m = pl->cap;
     rc = stabgpu_plan_upload(pl, m, s1 + 2 * (size_t)p0, s2 + 2 * (size_t)p0, Re_pt ? Re_pt + p0 : nullptr, Ma_pt ? Ma_pt + p0 : nullptr);
+    pl->evec_host = want_vectors ? evec + 2 * (size_t)p0 * N * N : nullptr;   // D2H of the vectors overlaps the eigenvector stage
     if (!rc) rc = stabgpu_plan_execute(pl);
-    if (!rc) rc = stabgpu_plan_download(pl, eig + 2 * (size_t)p0 * N, want_vectors ? evec + 2 * (size_t)p0 * N * N : nullptr,
-                                        info ? info + p0 : nullptr);
+    pl->evec_host = nullptr;
+    if (!rc) rc = stabgpu_plan_download(pl, eig + 2 * (size_t)p0 * N, nullptr, info ? info + p0 : nullptr);
   }
   return rc;
 }
