@@ -55,6 +55,9 @@ int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_th
 int stabgpu_set_hess_mode(int mode);
 /* eigenvector stage variant: 1 (default) register-resident inverse iteration + tensor-core back-transformation; 0 the v1 warp kernel */
 int stabgpu_set_evec_mode(int mode);
+/* spatial LU reduce variant (ZGETRF + 2 x ZGETRS, spatial.f90:978-1004): 1 (default) blocked LU with DMMA rank-32
+ * updates; 0 the v1 one-CTA-per-matrix kernel */
+int stabgpu_set_lu_mode(int mode);
 
 /* ---- host-side pieces of the path (pure C++, no device) ------------------------------------------ */
 void stabgpu_params_default(stabgpu_params* p);                       /* stuff.f90 initial values */
@@ -129,7 +132,9 @@ int stabgpu_plan_create(stabgpu_plan** plan, int kind, const stabgpu_params* p, 
                         const double* h5, int max_pts, int want_vectors);
 int stabgpu_plan_upload(stabgpu_plan* plan, int npts, const double* s1 /* alpha|omega */, const double* s2 /* beta */,
                         const double* Re_pt, const double* Ma_pt);              /* H2D of the sweep values */
-int stabgpu_plan_execute(stabgpu_plan* plan);                                    /* kernels only, async + sync */
+int stabgpu_plan_execute(stabgpu_plan* plan);                                    /* kernels only: enqueue + wait */
+int stabgpu_plan_enqueue(stabgpu_plan* plan);                                    /* launches every kernel of one pass on the plan's stream and returns */
+int stabgpu_plan_wait(stabgpu_plan* plan);                                       /* waits for the enqueued pass; fills the stage times */
 int stabgpu_plan_download(stabgpu_plan* plan, double* eig, double* evec, int* info); /* D2H */
 int stabgpu_plan_stage_times(stabgpu_plan* plan, float* ms /* 8 floats */);      /* CUDA-event time per stage of the last execute */
 long long stabgpu_plan_launch_count(stabgpu_plan* plan);

@@ -26,6 +26,7 @@ from .binding import (  # noqa: F401
     set_tuning,
     set_hess_mode,
     set_evec_mode,
+    set_lu_mode,
     sgengrid,
     shard_range,
     spatial_assemble,
@@ -36,6 +37,7 @@ from .binding import (  # noqa: F401
     write_eig_file,
     zgeev_batch,
     debug_stages,
+    debug_spatial_reduce,
 )
 from .api import Case, read_deck, spatial, temporal, mtemporal, mspatial  # noqa: F401
 from . import post  # noqa: F401

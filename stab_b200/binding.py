@@ -75,6 +75,7 @@ def lib():
     proto("stabgpu_set_tuning", i, [i, i, i, i])
     proto("stabgpu_set_hess_mode", i, [i])
     proto("stabgpu_set_evec_mode", i, [i])
+    proto("stabgpu_set_lu_mode", i, [i])
     proto("stabgpu_params_default", None, [_pp])
     proto("stabgpu_edge_properties", i, [_pp, d])
     proto("stabgpu_sgengrid", i, [i, d, d, vp, vp, vp, vp])
@@ -92,9 +93,12 @@ def lib():
     proto("stabgpu_temporal_assemble", i, [_pp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
     proto("stabgpu_spatial_assemble", i, [_pp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
     proto("stabgpu_debug_stages", i, [i, vp, vp, vp, _ip, _ip, vp, vp])
+    proto("stabgpu_debug_spatial_reduce", i, [_pp, vp, vp, vp, vp, vp, vp, vp, vp, vp, _ip])
     proto("stabgpu_plan_create", i, [C.POINTER(vp), i, _pp, vp, vp, vp, vp, vp, vp, i, i])
     proto("stabgpu_plan_upload", i, [vp, i, vp, vp, vp, vp])
     proto("stabgpu_plan_execute", i, [vp])
+    proto("stabgpu_plan_enqueue", i, [vp])
+    proto("stabgpu_plan_wait", i, [vp])
     proto("stabgpu_plan_download", i, [vp, vp, vp, vp])
     proto("stabgpu_plan_stage_times", i, [vp, C.POINTER(C.c_float)])
     proto("stabgpu_plan_launch_count", C.c_longlong, [vp])
@@ -249,6 +253,10 @@ def set_evec_mode(mode: int):
     lib().stabgpu_set_evec_mode(int(mode))
 
 
+def set_lu_mode(mode: int):
+    lib().stabgpu_set_lu_mode(int(mode))
+
+
 def _grid_args(p: Params, vm, g2vm, g22vm, deta, d2eta):
     ny = p.ny
     vmc = _colmajor(_f64(vm, (ny, 5)))
@@ -344,6 +352,19 @@ def spatial_assemble(p: Params, vm, deta, d2eta, omega: complex, beta: complex, 
     return tuple(c.T for c in Cs)
 
 
+def debug_spatial_reduce(p: Params, vm, deta, d2eta, omega: complex, beta: complex, h5=None, g2vm=None, g22vm=None):
+    """[M1 | M2] = C0^-1 [-C1 | -C2] (n x 2n) as the LU stage leaves it (spatial.f90:978-1008), and ZGETRF's info."""
+    vmc, g2c, g22c, de, d2e = _grid_args(p, vm, g2vm, g22vm, deta, d2eta)
+    h5c = None if h5 is None else _colmajor(_f64(h5, (p.ny, 5)))
+    n = NDOF * p.ny
+    M = np.empty((2 * n, n), dtype=np.complex128)
+    om, be = _c128(omega), _c128(beta)
+    info = C.c_int(0)
+    _check(lib().stabgpu_debug_spatial_reduce(C.byref(p), _ptr(vmc), _ptr(g2c), _ptr(g22c), _ptr(de), _ptr(d2e), _ptr(h5c),
+                                              _ptr(om), _ptr(be), _ptr(M), C.byref(info)), "stabgpu_debug_spatial_reduce")
+    return M.T, int(info.value)
+
+
 def temporal_polish(p: Params, vm, deta, d2eta, alpha: complex, beta: complex, sigma: complex, x0=None, max_iters: int = 8,
                     tol: float = 1e-13, g2vm=None, g22vm=None):
     """stabgpu_temporal_polish: shift-invert inverse iteration near `sigma` on (A0, B0).
@@ -399,6 +420,13 @@ class Plan:
 
     def execute(self):
         _check(lib().stabgpu_plan_execute(self._h), "stabgpu_plan_execute")
+
+    def enqueue(self):
+        """Launch one pass on the plan's stream without waiting (pair with wait())."""
+        _check(lib().stabgpu_plan_enqueue(self._h), "stabgpu_plan_enqueue")
+
+    def wait(self):
+        _check(lib().stabgpu_plan_wait(self._h), "stabgpu_plan_wait")
 
     def download(self, eig: Optional[np.ndarray] = None, evec: Optional[np.ndarray] = None, info: Optional[np.ndarray] = None):
         """Buffers may be preallocated (e.g. pinned); evec buffer layout is (npts, col, row)."""

@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../include/stabgpu.h"
 #include "kernels.cuh"
+#include "lu_blocked.cuh"
 
 using namespace stab;
 
@@ -17,7 +18,7 @@ thread_local std::string g_err;
 int g_device = -1;
 int g_sm_count = 148;
 bool g_inited = false;
-struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int hess_streams = 1; int evec_mode = 1; int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
+struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int hess_streams = 1; int evec_mode = 1; int lu_mode = 1; /* 1: blocked LU with DMMA updates, 0: v1 one-CTA kernel */ int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
 bool g_qrprof_on = false;
@@ -92,6 +93,7 @@ struct stabgpu_plan {
   cudaEvent_t evSub[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double* evec_host = nullptr;            // when set (batch C-ABI calls): eigenvectors are copied to the host per sub-batch, overlapped
   std::vector<cudaEvent_t> evA, evB;
+  bool stop_after_lu = false;             // debug: assembly + LU reduce only (stabgpu_debug_spatial_reduce)
   bool prof_hess = false;                 // record events around every Hessenberg kernel class (bench breakdown)
   std::vector<cudaEvent_t> pev; size_t pev_n = 0; std::vector<int> pev_cls;
   float hess_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // panel_step, gemv, gemm, other, invit, back-transformation GEMM, finalize, -
@@ -439,6 +441,46 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
   return 0;
 }
 
+// stage 2 (spatial): blocked LU reduce  A(0:n, :) <- C0^-1 A(0:n, :)  (lu_blocked.cuh)
+int run_lu_blocked(stabgpu_plan* pl) {
+  const int n = pl->n, N = pl->N, np = pl->npts;
+  cudaStream_t s = pl->stream;
+  LuBatch lb{pl->C.p, (size_t)n * n, n, pl->A.p, (size_t)N * N, N, N, pl->cnt.p, pl->info_lu.p};
+  CU(cudaMemsetAsync(pl->info_lu.p, 0, sizeof(int) * np, s));
+  const size_t sm_trsm = sizeof(cplx) * (LU_NB * LU_TRSM_THREADS + LU_NB * LU_NB) + sizeof(int) * LU_NB;
+  const size_t sm_gemm = PipeCfg<64, 32>::smem_bytes;
+  CU(cudaFuncSetAttribute(k_lu_swap_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trsm));
+  CU(cudaFuncSetAttribute(k_lu_back_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trsm));
+  CU(cudaFuncSetAttribute(k_lu_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gemm));
+  CU(cudaFuncSetAttribute(k_lu_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gemm));
+  auto gemm_grid = [&](long long total) { long long g = 2LL * g_sm_count; return (int)(g < total ? g : total); };
+  for (int j0 = 0; j0 < n; j0 += LU_NB) {
+    const int jb = (n - j0 < LU_NB) ? n - j0 : LU_NB, r0 = j0 + jb, ncols = (n - r0) + N;
+    k_lu_panel<<<np, 512, 0, s>>>(lb, j0);
+    k_lu_swap_trsm<<<dim3((ncols + LU_TRSM_THREADS - 1) / LU_TRSM_THREADS, np), LU_TRSM_THREADS, sm_trsm, s>>>(lb, j0);
+    pl->launches += 2;
+    if (r0 < n) {
+      const int ti = (n - r0 + 63) / 64, tj = (N + 31) / 32;
+      k_lu_gemm<0><<<gemm_grid((long long)ti * tj * 2 * np), GEMM_THREADS, sm_gemm, s>>>(lb, j0, ti, tj, 2 * np);
+      pl->launches += 1;
+    }
+    CU(cudaGetLastError());
+  }
+  const int nblk = (n + LU_NB - 1) / LU_NB;
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int i0 = b * LU_NB, bs = (n - i0 < LU_NB) ? n - i0 : LU_NB;
+    k_lu_back_trsm<<<dim3((N + LU_TRSM_THREADS - 1) / LU_TRSM_THREADS, np), LU_TRSM_THREADS, sm_trsm, s>>>(lb, i0, bs);
+    pl->launches += 1;
+    if (i0 > 0) {
+      const int ti = (i0 + 63) / 64, tj = (N + 31) / 32;
+      k_lu_gemm<1><<<gemm_grid((long long)ti * tj * np), GEMM_THREADS, sm_gemm, s>>>(lb, i0, ti, tj, np);
+      pl->launches += 1;
+    }
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
 // the eigen-pipeline on pl->A (npts matrices of order N): balance -> Hessenberg -> QR -> sort [-> vectors]
 int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   const int N = pl->N, np = pl->npts;
@@ -563,6 +605,7 @@ int stabgpu_debug_qr_profile(int enable, long long* out16) {
 int stabgpu_set_hess_mode(int mode) { g_tune.hess_mode = mode; return 0; }
 int stabgpu_debug_set_qr_steps(int steps) { if (steps > 0) g_tune.qr_steps = steps; return 0; }
 int stabgpu_set_evec_mode(int mode) { g_tune.evec_mode = mode; return 0; }
+int stabgpu_set_lu_mode(int mode) { g_tune.lu_mode = mode; return 0; }
 
 int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads) {
   if (qr_window > 0) g_tune.W = qr_window;
@@ -599,7 +642,7 @@ int stabgpu_plan_upload(stabgpu_plan* pl, int npts, const double* s1, const doub
   return 0;
 }
 
-int stabgpu_plan_execute(stabgpu_plan* pl) {
+int stabgpu_plan_enqueue(stabgpu_plan* pl) {
   if (!pl || pl->npts < 1) return fail("libstabgpu: plan_execute without uploaded points");
   const int np = pl->npts, ny = pl->ny, n = pl->n, N = pl->N;
   cudaStream_t s = pl->stream;
@@ -626,14 +669,25 @@ int stabgpu_plan_execute(stabgpu_plan* pl) {
     k_assemble_spatial<<<agrid, ASM_ROWS, 0, s>>>(g, pl->coef.p, pl->C.p, (size_t)n * n, pl->A.p, (size_t)N * N);
     CU(cudaGetLastError());
     CU(cudaEventRecord(pl->ev[ST_ASM + 1], s));
-    size_t sm = 160 * sizeof(double) + (size_t)n * sizeof(cplx);
-    k_lu<<<np, 512, sm, s>>>(pl->C.p, (size_t)n * n, n, pl->A.p, (size_t)N * N, N, N, pl->info_lu.p);
-    CU(cudaGetLastError());
+    if (g_tune.lu_mode == 1) {
+      if (run_lu_blocked(pl)) return 1;
+    } else {
+      size_t sm = 160 * sizeof(double) + (size_t)n * sizeof(cplx);
+      k_lu<<<np, 512, sm, s>>>(pl->C.p, (size_t)n * n, n, pl->A.p, (size_t)N * N, N, N, pl->info_lu.p);
+      CU(cudaGetLastError());
+      pl->launches += 1;
+    }
     CU(cudaEventRecord(pl->ev[ST_LU + 1], s));
-    pl->launches += 3;
+    pl->launches += 2;
+    if (pl->stop_after_lu) return 0;
     if (run_eigen(pl, 2, 0)) return 1;
   }
-  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int stabgpu_plan_wait(stabgpu_plan* pl) {
+  if (!pl) return fail("libstabgpu: null plan");
+  CU(cudaStreamSynchronize(pl->stream));
   if (pl->prof_hess && pl->pev_n > 1) {
     for (int c = 0; c < 8; ++c) pl->hess_ms[c] = 0.f;
     for (size_t i = 1; i < pl->pev_n; ++i) {
@@ -648,6 +702,11 @@ int stabgpu_plan_execute(stabgpu_plan* pl) {
     pl->ms[i] = t;
   }
   return 0;
+}
+
+int stabgpu_plan_execute(stabgpu_plan* pl) {
+  if (stabgpu_plan_enqueue(pl)) return 1;
+  return stabgpu_plan_wait(pl);
 }
 
 int stabgpu_plan_download(stabgpu_plan* pl, double* eig, double* evec, int* info) {
@@ -879,6 +938,24 @@ int stabgpu_spatial_assemble(const stabgpu_params* p, const double* vm, const do
                              const double* deta, const double* d2eta, const double* h5, const double* omega,
                              const double* beta, double* C0, double* C1, double* C2) {
   return inspect_common(2, p, vm, g2vm, g22vm, deta, d2eta, h5, omega, beta, C0, C1, C2);
+}
+
+/* debug / parity: the reduced spatial operator [M1 | M2] = C0^-1 [-C1 | -C2] (n x 2n, column-major) of one point, as the
+ * LU stage leaves it in the top half of the companion matrix (spatial.f90:978-1008) */
+int stabgpu_debug_spatial_reduce(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                                 const double* deta, const double* d2eta, const double* h5, const double* omega,
+                                 const double* beta, double* M, int* info) {
+  stabgpu_plan* pl = nullptr;
+  if (stabgpu_plan_create(&pl, 2, p, vm, g2vm, g22vm, deta, d2eta, h5, 1, 0)) return 1;
+  int rc = stabgpu_plan_upload(pl, 1, omega, beta, nullptr, nullptr);
+  pl->stop_after_lu = true;
+  if (!rc) rc = stabgpu_plan_enqueue(pl);
+  if (!rc) rc = cudaStreamSynchronize(pl->stream) != cudaSuccess;
+  const int n = pl->n, N = pl->N;
+  if (!rc) rc = cudaMemcpy2D(M, sizeof(cplx) * n, pl->A.p, sizeof(cplx) * N, sizeof(cplx) * n, N, cudaMemcpyDeviceToHost) != cudaSuccess;
+  if (!rc && info) rc = cudaMemcpy(info, pl->info_lu.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess;
+  stabgpu_plan_destroy(pl);
+  return rc ? fail("libstabgpu: debug_spatial_reduce failed") : 0;
 }
 
 int stabgpu_temporal_polish(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,

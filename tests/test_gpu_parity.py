@@ -297,6 +297,42 @@ def test_spatial_golden_cf_ny64():
                    _rows("cf_spatial_ny64.space.ref"), tol_rows=1e-8)
 
 
+@pytest.mark.parametrize("deck,prof,over", [
+    ("ts_spatial_ny32.inp", "ts_profile.0", dict()),                 # n = 160 = 5 panels
+    ("ts_spatial_ny32.inp", "ts_profile.0", dict(ny=27)),            # n = 135: ragged last panel
+    ("ts_spatial_ny32.inp", "ts_profile.0", dict(ny=5)),             # n = 25 < one panel
+    ("cf_spatial_ny96.inp", "cf_profile.0", dict(ny=64)),            # M=0.8, Re=1e5, beta=35: row interchanges matter
+    ("fsc_spatial_ny64.inp", "fsc_profile.0", dict(ny=128)),         # BASELINE size n = 640
+])
+def test_spatial_lu_reduce_blocked(deck, prof, over):
+    """Stage 2 (ZGETRF + 2 x ZGETRS, spatial.f90:978-1008): the blocked DMMA LU reduce against LAPACK on the same C0, C1, C2
+    and against the v1 one-CTA kernel; error bound = the backward-stable bound eps * cond(C0) relative to |M|."""
+    import scipy.linalg as sla
+    p, g = oracle_case(deck, prof, **over)
+    P = to_params(p)
+    C0, C1, C2 = sb.spatial_assemble(P, g["vm"], g["deta"], g["d2eta"], p.omega, p.beta, h5=g["h5"])
+    n = C0.shape[0]
+    lu, piv = sla.lu_factor(C0)
+    ref = sla.lu_solve((lu, piv), np.hstack([-C1, -C2]))
+    M, info = sb.debug_spatial_reduce(P, g["vm"], g["deta"], g["d2eta"], p.omega, p.beta, h5=g["h5"])
+    assert info == 0 and M.shape == (n, 2 * n)
+    sb.set_lu_mode(0)
+    try:
+        M0, info0 = sb.debug_spatial_reduce(P, g["vm"], g["deta"], g["d2eta"], p.omega, p.beta, h5=g["h5"])
+    finally:
+        sb.set_lu_mode(1)
+    assert info0 == 0
+    # residual of the defining equation, the quantity partial pivoting bounds: C0 M = -[C1 C2]
+    rhs = np.hstack([-C1, -C2])
+    scale = np.linalg.norm(C0, 1) * np.abs(ref).max() + np.abs(rhs).max()
+    assert np.abs(C0 @ M - rhs).max() / scale < 1e-13
+    assert np.abs(C0 @ M0 - rhs).max() / scale < 1e-13
+    cond = np.linalg.cond(C0, 1)
+    tol = 50 * n * np.finfo(float).eps * cond
+    assert np.abs(M - ref).max() / np.abs(ref).max() < max(tol, 1e-13)
+    assert np.abs(M - M0).max() / np.abs(ref).max() < max(tol, 1e-13)
+
+
 def test_spatial_omega_sweep_readme_values():
     # TStest/README.md:9 (Ny=64); batch over omega, eigenvalues only (ievec=0)
     p, g = oracle_case("ts_spatial_ny96.inp", "ts_profile.0", ny=64, ievec=0)
