@@ -35,19 +35,22 @@ SD_DEV cplx shfl_c(cplx v, int src) { return mk(__shfl_sync(0xffffffffu, v.re, s
 
 // One elimination step k with the boundary slot index SB = k >> 5 known at compile time: rows < 32*SB
 // (slots 0..SB-1, or 0..SB-2 when k is a multiple of 32) are updated branch-free on registers.
-template <int NS, int SB>
-SD_DEV void invit_step(int k, int lane, const cplx* __restrict__ acol, cplx lm, double eps3, cplx (&c)[NS], cplx (&y)[NS],
-                       unsigned& flags, cplx& cdiag, cplx& ydiag) {
-  const cplx ak = acol[k];
-  const bool sw = cabs1(ak) > cabs1(cdiag);
+// pivot decision of step k: ak = H(k, k-1) against the carried column's entry in row k
+SD_DEV void invit_pivot(cplx ak, cplx cdiag, cplx ydiag, double eps3, bool& sw, cplx& mq, cplx& yk) {
+  sw = cabs1(ak) > cabs1(cdiag);
   cplx piv = sw ? ak : cdiag;
   if (is_zero(piv)) piv = mk(eps3, 0.0);
   // 1/piv = conj(piv)/|piv|^2: pivots are O(eps3)..O(||H||), their squares are far from the
   // overflow/underflow thresholds, so Smith's dependent divisions are not needed here
   const double rd = __drcp_rn(fma(piv.re, piv.re, piv.im * piv.im));
   const cplx inv = mk(piv.re * rd, -piv.im * rd);
-  const cplx yk = ydiag * inv;
-  const cplx mq = (sw ? cdiag : ak) * inv;
+  yk = ydiag * inv;
+  mq = (sw ? cdiag : ak) * inv;
+}
+
+template <int NS, int SB>
+SD_DEV void invit_apply(int k, int lane, const cplx* __restrict__ acol, cplx lm, bool sw, cplx mq, cplx yk, cplx (&c)[NS], cplx (&y)[NS],
+                        unsigned& flags, cplx& cdiag, cplx& ydiag) {
   cplx cnext = mk(0.0, 0.0), ynext = mk(0.0, 0.0);
   const bool edge = (k & 31) == 0;                   // row k-1 lives in slot SB-1 (lane 31)
   // (1) boundary slot(s): diagonal shift, pivot capture, multiplier store
@@ -99,6 +102,14 @@ SD_DEV void invit_step(int k, int lane, const cplx* __restrict__ acol, cplx lm, 
       c[SB > 0 ? SB - 1 : 0] = a;
     }
   }
+}
+
+template <int NS, int SB>
+SD_DEV void invit_step(int k, int lane, const cplx* __restrict__ acol, cplx lm, double eps3, cplx (&c)[NS], cplx (&y)[NS],
+                       unsigned& flags, cplx& cdiag, cplx& ydiag) {
+  bool sw; cplx mq, yk;
+  invit_pivot(acol[k], cdiag, ydiag, eps3, sw, mq, yk);
+  invit_apply<NS, SB>(k, lane, acol, lm, sw, mq, yk, c, y, flags, cdiag, ydiag);
 }
 
 // The 32 steps k = 32*SB+31 .. 32*SB (four staged 8-column blocks), then recurse to SB-1.
@@ -244,6 +255,218 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
         if (r < n) out[r] = (r < m) ? y[s] : mk(0.0, 0.0);
       }
       if (lane == 0) bad[(size_t)p * n + e] = isbad;
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Orders 32 NSH < n <= 64 NSH (the spatial companion problem at Ny = 128, n = 1280; Ny = 256 temporal): TWO warps per
+// eigenvalue.  Warp F owns rows [0, R0), warp P rows [R0, 2 R0), R0 = 32 NSH; both keep their part of the carried column
+// and of the right-hand side in registers, exactly as above.
+//   steps k >= R0 (the pivot row is P's): P takes the pivot decision, publishes (sw, mq, yk) through shared memory, both
+//                 warps meet at a 64-thread named barrier and apply the step to their rows -- F's rows are all above
+//                 the boundary, so its update is the plain bulk form (at k = R0 it also shifts the diagonal entry of
+//                 row R0-1 and takes over the carried diagonal);
+//   steps k <  R0: P's rows are finished (they hold multipliers); F runs the single-warp step.
+// The published values are double buffered by the parity of k, so P may run one step ahead of F.  Four eigenvalues per
+// CTA; the Hessenberg columns are staged in 4-column blocks (2 x 4 x n x 16 B = 160 KB at n = 1280).
+constexpr int INVIT2_CB = 4;
+constexpr int INVIT2_PAIRS = 4;
+
+SD_DEV void pair_barrier(int pi) { asm volatile("bar.sync %0, 64;" ::"r"(pi + 1) : "memory"); }
+
+struct Invit2Pub { cplx mq, yk; int sw; int pad; };
+
+template <int NSH>
+SD_DEV void invit_follow(bool last, int lane, const cplx* __restrict__ acol, cplx lm, bool sw, cplx mq, cplx yk,
+                         cplx (&c)[NSH], cplx (&y)[NSH], cplx& cdiag, cplx& ydiag) {
+  if (sw) {
+#pragma unroll
+    for (int s = 0; s < NSH; ++s) {
+      cplx a = acol[32 * s + lane];
+      if (s == NSH - 1 && last && lane == 31) a -= lm;
+      fms_acc(y[s], yk, a); fms_acc(c[s], mq, a);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < NSH; ++s) {
+      cplx a = acol[32 * s + lane];
+      if (s == NSH - 1 && last && lane == 31) a -= lm;
+      const cplx cr = c[s];
+      fms_acc(y[s], yk, cr); fms_acc(a, mq, cr);
+      c[s] = a;
+    }
+  }
+  if (last) { cdiag = shfl_c(c[NSH - 1], 31); ydiag = shfl_c(y[NSH - 1], 31); }
+}
+
+// the 32 steps k = 32 SBG + 31 .. 32 SBG (eight staged 4-column blocks), then recurse to SBG-1
+template <int NSH, int SBG>
+struct Invit2Slot {
+  template <class Prefetch>
+  SD_DEV static void run(int n, int m, bool live, int lane, int role, int pi, cplx* sH, Invit2Pub* pub, cplx lm, double eps3,
+                         cplx (&c)[NSH], cplx (&y)[NSH], unsigned& flags, cplx& cdiag, cplx& ydiag, int& buf, Prefetch& prefetch) {
+    constexpr int R0 = 32 * NSH;
+    for (int bq = 32 / INVIT2_CB - 1; bq >= 0; --bq) {
+      const int B = (32 / INVIT2_CB) * SBG + bq;
+      if (INVIT2_CB * B > n - 1) continue;                 // block above the matrix (uniform)
+      cp_async_wait<0>();
+      __syncthreads();                                     // block B landed; everyone left block B+1
+      if (B > 0) prefetch(B - 1, buf ^ 1);
+      const cplx* tile = sH + (size_t)buf * INVIT2_CB * n;
+      for (int q = INVIT2_CB - 1; q >= 0; --q) {
+        const int k = INVIT2_CB * B + q;
+        if (k > n - 1 || k < 1) continue;
+        if (!live || k > m - 1) continue;                  // same for both warps of a pair
+        const cplx* acol = tile + (size_t)q * n;
+        if (SBG >= NSH) {                                  // pivot row in P's range
+          Invit2Pub* pb = pub + 2 * pi + (k & 1);
+          if (role == 1) {
+            bool sw; cplx mq, yk;
+            invit_pivot(acol[k], cdiag, ydiag, eps3, sw, mq, yk);
+            if (lane == 0) { pb->mq = mq; pb->yk = yk; pb->sw = sw ? 1 : 0; }
+            pair_barrier(pi);
+            invit_apply<NSH, (SBG >= NSH ? SBG - NSH : 0)>(k - R0, lane, acol + R0, lm, sw, mq, yk, c, y, flags, cdiag, ydiag);
+          } else {
+            pair_barrier(pi);
+            const bool sw = pb->sw != 0;
+            const cplx mq = pb->mq, yk = pb->yk;
+            invit_follow<NSH>(k == R0, lane, acol, lm, sw, mq, yk, c, y, cdiag, ydiag);
+          }
+        } else if (role == 0) {
+          invit_step<NSH, (SBG < NSH ? SBG : 0)>(k, lane, acol, lm, eps3, c, y, flags, cdiag, ydiag);
+        }
+      }
+      buf ^= 1;
+    }
+    Invit2Slot<NSH, SBG - 1>::run(n, m, live, lane, role, pi, sH, pub, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+  }
+};
+template <int NSH>
+struct Invit2Slot<NSH, -1> {
+  template <class Prefetch>
+  SD_DEV static void run(int, int, bool, int, int, int, cplx*, Invit2Pub*, cplx, double, cplx (&)[NSH], cplx (&)[NSH], unsigned&, cplx&, cplx&,
+                         int&, Prefetch&) {}
+};
+
+// grid: (ceil(n / (4*rounds)), batch), block 256.  smem: 2 * INVIT2_CB * n complex + INVIT2_PAIRS * n bytes.  n <= 64 NSH.
+template <int NSH>
+__global__ void __launch_bounds__(INVIT2_PAIRS * 64, 1)
+k_invit2(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restrict__ lam, const int* __restrict__ kr,
+         const double* __restrict__ hnorm, cplx* __restrict__ Y, size_t ystride, int* __restrict__ bad, int rounds) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ Invit2Pub pub[2 * INVIT2_PAIRS];
+  __shared__ double vnorm[2 * INVIT2_PAIRS];
+  constexpr int R0 = 32 * NSH;
+  cplx* sH = reinterpret_cast<cplx*>(smem_raw);            // [2][INVIT2_CB][n]
+  const int p = blockIdx.y;
+  const cplx* H = Hh + (size_t)p * hstride;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, pi = wid >> 1, role = wid & 1;
+  const int rbase = role * R0;                             // first row this warp owns
+  const double smlnum = SD_SAFMIN * ((double)n / SD_ULP);
+  const double eps3 = fmax(SD_ULP * hnorm[p], smlnum);
+  const double growto = 0.1 / sqrt((double)n);
+
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int e = (blockIdx.x * rounds + rd) * INVIT2_PAIRS + pi;
+    const bool live = e < n;
+    const int m = live ? kr[(size_t)p * n + e] + 1 : 0;     // leading block order
+    const cplx lm = live ? lam[(size_t)p * n + e] : mk(0.0, 0.0);
+    cplx c[NSH], y[NSH];
+#pragma unroll
+    for (int s = 0; s < NSH; ++s) { c[s] = mk(0.0, 0.0); y[s] = mk(0.0, 0.0); }
+    unsigned flags = 0u;
+    cplx cdiag = mk(0.0, 0.0), ydiag = mk(0.0, 0.0);
+
+    // block B covers steps k = 4B+3 .. 4B, i.e. columns k-1, rows 0..k of each; tile column q <-> step k = 4B+q
+    auto prefetch = [&](int B, int bufi) {
+      cplx* dst = sH + (size_t)bufi * INVIT2_CB * n;
+      for (int q = 0; q < INVIT2_CB; ++q) {
+        const int k = INVIT2_CB * B + q;
+        if (k < 1 || k > n - 1) continue;
+        const cplx* src = H + (size_t)(k - 1) * n;
+        for (int r = threadIdx.x; r <= k; r += blockDim.x) cp_async16(dst + (size_t)q * n + r, src + r);
+      }
+      cp_async_commit();
+    };
+    if (live) {                                             // start: carried column = column m-1 of H - lam I
+      const cplx* hc = H + (size_t)(m - 1) * n;
+#pragma unroll
+      for (int s = 0; s < NSH; ++s) {
+        const int r = rbase + 32 * s + lane;
+        if (r < m) {
+          cplx a = hc[r];
+          if (r == m - 1) a -= lm;
+          c[s] = a; y[s] = mk(eps3, 0.0);
+        }
+      }
+      cdiag = hc[m - 1] - lm;
+      ydiag = mk(eps3, 0.0);
+    }
+    __syncthreads();                                        // previous round finished with both buffers
+    int buf = 0;
+    prefetch((n - 1) / INVIT2_CB, 0);
+    Invit2Slot<NSH, 2 * NSH - 1>::run(n, m, live, lane, role, pi, sH, pub, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+    // ---- x = T_{m-1} ... T_1 y: the first-order recurrence of the single-warp kernel, run by lane 0 of warp F over
+    // the rows of both warps (parked in the idle staging buffers) ----
+    __syncthreads();                                        // every warp has finished reading the staged columns
+    if (live) {
+      cplx* wy = sH + (size_t)pi * 2 * n;
+      cplx* wc = wy + n;
+      unsigned char* wf = reinterpret_cast<unsigned char*>(sH + (size_t)2 * INVIT2_CB * n) + (size_t)pi * n;
+#pragma unroll
+      for (int s = 0; s < NSH; ++s) {
+        const int r = rbase + 32 * s + lane;
+        if (r < m) { wy[r] = y[s]; wc[r] = c[s]; wf[r] = (unsigned char)((flags >> s) & 1u); }
+      }
+      pair_barrier(pi);
+      if (role == 0 && lane == 0) {
+        cplx piv = cdiag;
+        if (is_zero(piv)) piv = mk(eps3, 0.0);
+        cplx prev = cdiv(ydiag, piv);                       // current value of y[k-1]
+        int k = 1;
+        for (; k + 3 < m; k += 4) {                         // loads of four rows in flight, recurrence in order
+          const cplx y0 = wy[k], y1 = wy[k + 1], y2 = wy[k + 2], y3 = wy[k + 3];
+          const cplx m0 = wc[k], m1 = wc[k + 1], m2 = wc[k + 2], m3 = wc[k + 3];
+          const bool f0 = wf[k] != 0, f1 = wf[k + 1] != 0, f2 = wf[k + 2] != 0, f3 = wf[k + 3] != 0;
+          cplx t, fin;
+          t = y0 - m0 * prev; fin = f0 ? t : prev; prev = f0 ? prev : t; wy[k - 1] = fin;
+          t = y1 - m1 * prev; fin = f1 ? t : prev; prev = f1 ? prev : t; wy[k] = fin;
+          t = y2 - m2 * prev; fin = f2 ? t : prev; prev = f2 ? prev : t; wy[k + 1] = fin;
+          t = y3 - m3 * prev; fin = f3 ? t : prev; prev = f3 ? prev : t; wy[k + 2] = fin;
+        }
+        for (; k < m; ++k) {
+          const cplx t = wy[k] - wc[k] * prev;
+          const bool f = wf[k] != 0;
+          const cplx fin = f ? t : prev;                    // final x[k-1]
+          prev = f ? prev : t;
+          wy[k - 1] = fin;
+        }
+        wy[m - 1] = prev;                                   // last row gets the carried value
+      }
+      pair_barrier(pi);
+#pragma unroll
+      for (int s = 0; s < NSH; ++s) {
+        const int r = rbase + 32 * s + lane;
+        if (r < m) y[s] = wy[r];
+      }
+      double vn = 0.0;
+#pragma unroll
+      for (int s = 0; s < NSH; ++s)
+        if (rbase + 32 * s + lane < m) vn += cabs1(y[s]);
+      vn = warp_sum(vn);
+      if (lane == 0) vnorm[wid] = vn;
+      pair_barrier(pi);
+      vn = vnorm[2 * pi] + vnorm[2 * pi + 1];
+      const int isbad = (!(vn == vn) || vn > 1.0e300 || vn < growto) ? 1 : 0;
+      cplx* out = Y + (size_t)p * ystride + (size_t)e * n;
+#pragma unroll
+      for (int s = 0; s < NSH; ++s) {
+        const int r = rbase + 32 * s + lane;
+        if (r < n) out[r] = (r < m) ? y[s] : mk(0.0, 0.0);
+      }
+      if (role == 0 && lane == 0) bad[(size_t)p * n + e] = isbad;
     }
   }
 }

@@ -348,7 +348,22 @@ int launch_invit(stabgpu_plan* pl, int rounds, int m0, int cnt) {
   return 0;
 }
 
-// Stage 6: right eigenvectors.  evec_mode 1 (default, N <= 640 and blocked Hessenberg factors available):
+// orders 640 < N <= 1280: two warps per eigenvalue (k_invit2)
+template <int NSH>
+int launch_invit2(stabgpu_plan* pl, int rounds, int m0, int cnt) {
+  const int N = pl->N;
+  const size_t st = (size_t)N * N;
+  const size_t sm = 2 * (size_t)INVIT2_CB * N * sizeof(cplx) + (size_t)INVIT2_PAIRS * N;
+  CU(cudaFuncSetAttribute(k_invit2<NSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid((N + INVIT2_PAIRS * rounds - 1) / (INVIT2_PAIRS * rounds), cnt);
+  k_invit2<NSH><<<grid, INVIT2_PAIRS * 64, sm, pl->stream>>>(pl->A.p + (size_t)m0 * st, st, N, pl->lam.p + (size_t)m0 * N, pl->kr.p + (size_t)m0 * N,
+                                                             pl->hnorm.p + m0, pl->V.p + (size_t)m0 * st, st, pl->vbad.p + (size_t)m0 * N, rounds);
+  CU(cudaGetLastError());
+  pl->launches += 1;
+  return 0;
+}
+
+// Stage 6: right eigenvectors.  evec_mode 1 (default, N <= 1280 and blocked Hessenberg factors available):
 // register-resident inverse iteration -> GEMM back-transformation -> finalize; otherwise the v1 warp kernel.
 // The batch is processed in sub-batches; when the caller registered a host destination (the batch C-ABI calls), the
 // finished vectors of sub-batch i travel to the host on the copy stream while sub-batch i+1 is computed.
@@ -363,7 +378,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
   const size_t sm_old = warps * per_warp;
   if (sm_old > 227 * 1024) return fail("libstabgpu: matrix too large for the eigenvector kernel");
   CU(cudaFuncSetAttribute(k_evec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_old));
-  const bool fast = g_tune.evec_mode == 1 && g_tune.hess_mode != 0 && N <= 640;
+  const bool fast = g_tune.evec_mode == 1 && g_tune.hess_mode != 0 && N <= 1280;
   const int nsub = !pl->evec_host ? 1 : (np >= 8 * 37 ? 8 : (np >= 4 * 37 ? 4 : (np >= 2 ? 2 : 1)));   // >= 37 matrices per sub-batch keep the kernels full
   if (hmark(pl, s, 7)) return 1;               // start marker of the eigenvector breakdown (class 7: not reported)
   for (int sb = 0; sb < nsub; ++sb) {
@@ -386,7 +401,9 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
       else if (N <= 256) rc = launch_invit<8>(pl, rounds, m0, cnt);
       else if (N <= 384) rc = launch_invit<12>(pl, rounds, m0, cnt);
       else if (N <= 512) rc = launch_invit<16>(pl, rounds, m0, cnt);
-      else rc = launch_invit<20>(pl, rounds, m0, cnt);
+      else if (N <= 640) rc = launch_invit<20>(pl, rounds, m0, cnt);
+      else if (N <= 1024) rc = launch_invit2<16>(pl, rounds, m0, cnt);
+      else rc = launch_invit2<20>(pl, rounds, m0, cnt);
       if (rc) return 1;
       // vectors the fast kernel rejected (no growth / overflow): ZLAEIN's retry vectors, v1 kernel, Hessenberg basis
       k_evec<<<grid_old, warps * 32, sm_old, s>>>(pl->A.p + (size_t)m0 * st, st, N, pl->ilohi.p + 2 * m0, pl->tau.p + (size_t)m0 * N,

@@ -126,6 +126,62 @@ def test_eigenvector_paths_agree():
     assert np.abs(V0 - V1).max() < 1e-10
 
 
+@pytest.mark.parametrize("n", [641, 700, 1024, 1280])
+def test_zgeev_batch_two_warp_eigenvectors(n):
+    """Orders 640 < n <= 1280 (spatial companion at Ny=128, temporal Ny=256): inverse iteration with two warps per
+    eigenvalue (k_invit2) + tensor-core back-transformation; residuals, ZGEEV normalisation, and the v1 kernel's vectors."""
+    A = _rand(n, 300 + n, 2)
+    w, V, info = sb.zgeev_batch(A, want_vectors=True)
+    assert np.all(info == 0)
+    for b in range(2):
+        ref = np.linalg.eigvals(A[b])
+        _, d = match_spectra(ref, w[b])
+        assert d.max() < 1e-11 * np.abs(ref).max()
+        assert eigpair_residuals(A[b], w[b], V[b]).max() < 4 * n * np.finfo(float).eps      # backward stable: O(n eps)
+        assert np.abs(np.linalg.norm(V[b], axis=0) - 1).max() < 1e-12
+    if n in (641, 700):
+        sb.set_evec_mode(0)
+        try:
+            w0, V0, i0 = sb.zgeev_batch(A[:1], want_vectors=True)
+        finally:
+            sb.set_evec_mode(1)
+        assert np.array_equal(w0[0], w[0])
+        assert np.abs(V0[0] - V[0]).max() < 1e-9
+
+
+def test_spatial_companion_vectors_ny72():
+    """Spatial problem with eigenvectors at companion order 2n = 720 (> 640: two-warp inverse iteration), block-triangular
+    structure (many exactly-zero eigenvalues, leading-block orders kr < n): residuals of every finite mode against the
+    oracle's companion matrix and the TS mode's eigenfunction against the oracle's."""
+    p, g = oracle_case("ts_spatial_ny96.inp", "ts_profile.0", ny=72, ievec=1)
+    alp, ev, info = sb.spatial_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], [p.omega], [p.beta], h5=g["h5"], want_vectors=True)
+    assert info[0] == 0
+    ref = so.solve_spatial(p, g["vm"], g["deta"], g["d2eta"], g["hm"], want_vectors=True)
+    target = complex(2.2804739411367E-001, -6.5163146912049E-003)     # TStest/README.md:10 (Ny=96 value)
+    j = so.select_mode(alp[0], target)
+    jr = so.select_mode(ref["alp"], target)
+    assert abs(alp[0][j] - ref["alp"][jr]) < 1e-10
+    n = 5 * p.ny
+    x, xr = ev[0][:n, j], ref["evec"][:n, jr]
+    x, xr = x / x[np.argmax(np.abs(x))], xr / xr[np.argmax(np.abs(xr))]
+    assert np.abs(x - xr).max() < 1e-8
+    M = ref["B0"]
+    fin = np.abs(alp[0]) > 1e-8
+    lam = np.where(fin, 1.0 / np.where(fin, alp[0], 1.0), 0.0)
+
+    def resid(vecs, lams):
+        R = M @ vecs - vecs * lams[None, :]
+        return np.linalg.norm(R, axis=0) / (np.linalg.norm(M) * np.linalg.norm(vecs, axis=0))
+    res = resid(ev[0], lam)
+    # Inverse iteration accepts a vector once it has grown by 0.1/sqrt(N) (ZLAEIN's criterion), which bounds the backward
+    # error by ~10 N^1.5 ulp ||H||_inf: attained only by the near-defective continuous-branch modes at alpha ~ omega/c
+    # (LAPACK's ZTREVC path gives ~5e-14 there); the discrete TS mode and the bulk of the spectrum sit at rounding level.
+    N = 2 * n
+    assert res[fin].max() < 10 * N ** 1.5 * np.finfo(float).eps * np.sqrt(N)
+    assert res[j] < 1e-13
+    assert np.median(res[fin]) < 1e-15
+
+
 def test_zgeev_batch_structured():
     """Matrices with isolated eigenvalues (balancing permutes), defective blocks and zero rows."""
     n = 40
