@@ -198,6 +198,17 @@ __global__ void __launch_bounds__(256, 2) k_balance(cplx* A, size_t astride, int
   cta_balance(c, A + (size_t)p * astride, n, n, scale + (size_t)p * n, cnt + (size_t)p * n, reinterpret_cast<double*>(smem_raw), bal_b, ilo, ihi);
   if (threadIdx.x == 0) { ilohi[2 * p] = ilo; ilohi[2 * p + 1] = ihi; }
 }
+// orders above 640 (spatial companion, Ny = 256): one CTA of 512 threads per SM, 8-index blocks while they fit
+SD_HD int balance_block_wide(int n) { return (size_t)144 * n <= 200 * 1024 ? 8 : balance_block(n); }
+__global__ void __launch_bounds__(512, 1) k_balance_wide(cplx* A, size_t astride, int n, double* scale, int* cnt, int* ilohi, int bal_b) {
+  __shared__ double red[160];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta c = make_cta(red);
+  const int p = blockIdx.x;
+  int ilo, ihi;
+  cta_balance(c, A + (size_t)p * astride, n, n, scale + (size_t)p * n, cnt + (size_t)p * n, reinterpret_cast<double*>(smem_raw), bal_b, ilo, ihi);
+  if (threadIdx.x == 0) { ilohi[2 * p] = ilo; ilohi[2 * p + 1] = ihi; }
+}
 
 // ---- stage 3b: Hessenberg -----------------------------------------------------------------------
 __global__ void k_hessenberg(cplx* A, size_t astride, int n, const int* ilohi, cplx* tau) {

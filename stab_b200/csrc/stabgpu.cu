@@ -503,7 +503,12 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   const int N = pl->N, np = pl->npts;
   const size_t st = (size_t)N * N;
   cudaStream_t s = pl->stream;
-  {
+  if (N > 640) {
+    const int bb = balance_block_wide(N);
+    const size_t smb = balance_wsp_doubles(N, bb) * sizeof(double);
+    CU(cudaFuncSetAttribute(k_balance_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+    k_balance_wide<<<np, 512, smb, s>>>(pl->A.p, st, N, pl->scale.p, pl->cnt.p, pl->ilohi.p, bb);
+  } else {
     const int bb = balance_block(N);
     const size_t smb = balance_wsp_doubles(N, bb) * sizeof(double);
     CU(cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
