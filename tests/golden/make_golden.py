@@ -37,6 +37,13 @@ COPIES = {
     "FSCtest/space.ref": "fsc_spatial_ny64.space.ref",
     "CFtest/input.dat": "cf_spatial_ny96.inp",
     "CFtest/space.ref": "cf_spatial_ny64.space.ref",
+    # the thesis crossflow case: decks of the external `fsc` mean-flow solver and the CI's golden eigenfunctions
+    "thesis/TStest/blasius.inp": "ts_thesis_fsc.inp",
+    "thesis/CFtest/fsc.inp": "cf_thesis_fsc.inp",
+    "thesis/CFtest/temporal.inp": "cf_thesis_temporal_ny96.inp",
+    "thesis/CFtest/time.ref": "cf_thesis_temporal_ny96.time.ref",
+    "thesis/CFtest/spatial.inp": "cf_thesis_spatial_ny96.inp",
+    "thesis/CFtest/space.ref": "cf_thesis_spatial_ny96.space.ref",
 }
 
 

@@ -24,13 +24,14 @@ def to_params(p: "so.Params") -> "sb.Params":
     return q
 
 
-def oracle_case(deck, prof, **over):
-    """deck + profile -> (oracle params, grid dict incl. hm/h5 for spatial)."""
+def oracle_case(deck, prof, profile_text=None, **over):
+    """deck + profile -> (oracle params, grid dict incl. hm/h5 for spatial).  `profile_text` overrides the golden
+    profile file (generated mean flows, stab_b200/fsc.py)."""
     p = so.read_deck(golden_text(deck))
     for k, v in over.items():
         setattr(p, k, v)
     p.finish()
-    g = so.prepare(p, golden_text(prof))
+    g = so.prepare(p, golden_text(prof) if profile_text is None else profile_text)
     if p.itype == 2:
         x_out, hm = so.curvature_metrics(p, g["y"])
         g["hm"] = hm

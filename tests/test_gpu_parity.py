@@ -267,6 +267,46 @@ def test_temporal_golden_thesis_time_ref():
     assert np.abs(rows - _rows("ts_temporal_ny96.time.ref")).max() < 1e-8
 
 
+def _cf_profile_text():
+    from stab_b200 import fsc
+    return fsc.format_table(fsc.profile_from_deck(golden_text("cf_thesis_fsc.inp"))["table"])
+
+
+def test_temporal_golden_thesis_crossflow_time_ref():
+    """thesis/CFtest (Collis thesis Ch. 4 crossflow vortex, M=0.3, Re=400, 45 deg sweep, beta_h=1) on the mean flow
+    GENERATED by stab_b200/fsc.py: eigenvalue of time.ref:2 / run.sh:13 and the 96-row eigenfunction."""
+    p, g = oracle_case("cf_thesis_temporal_ny96.inp", None, profile_text=_cf_profile_text())
+    omg, ev, info = sb.temporal_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], [p.alpha], [p.beta], want_vectors=True)
+    assert info[0] == 0
+    target = complex(6.3418480187508E-007, 6.5335847258858E-003)
+    j = so.select_mode(omg[0], target)
+    assert abs(omg[0][j] - target) < 1e-9
+    rows = so.getevec_rows(g["y"], ev[0][:, j], p.ny)
+    assert np.abs(rows - _rows("cf_thesis_temporal_ny96.time.ref")).max() < 5e-8     # see tests/test_fsc.py on the 5e-8
+    ref = so.solve_temporal(p, g["vm"], g["deta"], g["d2eta"], want_vectors=True)
+    jr = so.select_mode(ref["omg"], target)
+    assert abs(omg[0][j] - ref["omg"][jr]) < 1e-12
+    assert np.abs(rows - so.getevec_rows(g["y"], ref["evec"][:, jr], p.ny)).max() < 1e-9
+
+
+def test_temporal_crossflow_alpha_beta_grid_ny128():
+    """BASELINE configs[2]: crossflow-vortex temporal sweep over an (alpha, beta) grid at Ny=128 on the
+    generated Falkner-Skan-Cooke profile; mtemporal's enumeration; two points against the oracle, the unstable
+    crossflow mode to 1e-10 relative."""
+    p, g = oracle_case("cf_thesis_temporal_ny96.inp", None, profile_text=_cf_profile_text(), ny=128)
+    a, b = sb.mtemporal_points(-0.5, 0.0, 0.125, 0.1, 0.6, 0.125)
+    assert a.size == 4 * 4                       # both upper ends excluded (mtemporal.f90:25-39, quirk q6)
+    omg, ev, info = sb.temporal_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], a + 0j, b + 0j, want_vectors=False)
+    assert np.all(info == 0) and ev is None
+    for k in (5, 13):
+        p.alpha, p.beta = complex(a[k]), complex(b[k])
+        _check_temporal_point(p, g, omg[k], None, phys_tol=1e-10)
+    # the sweep contains amplified crossflow modes (Im omega > 0) around (alpha, beta) = (-0.25, 0.35)
+    k = int(np.argmin(np.abs(a + 0.25) + np.abs(b - 0.35)))
+    phys = np.abs(omg[k]) < 1.0
+    assert omg[k][phys].imag.max() > 1e-3
+
+
 def test_temporal_ny128_full_size_properties():
     """BASELINE config size (Ny=128, n=640): oracle comparison on 2 points + size-independent properties."""
     p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=128)
