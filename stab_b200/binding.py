@@ -439,6 +439,12 @@ class Plan:
         _check(lib().stabgpu_plan_download(self._h, _ptr(eig), _ptr(evec), _ptr(info)), "stabgpu_plan_download")
         return eig, (None if evec is None else _evec_out(evec)), info
 
+    def info(self) -> np.ndarray:
+        """Per-point LAPACK-style status of the last pass (no eigenvalue / eigenvector transfer)."""
+        info = np.zeros(self.npts, dtype=np.int32)
+        _check(lib().stabgpu_plan_download(self._h, None, None, _ptr(info)), "stabgpu_plan_download")
+        return info
+
     def stage_times(self) -> dict:
         ms = (C.c_float * 8)()
         lib().stabgpu_plan_stage_times(self._h, ms)

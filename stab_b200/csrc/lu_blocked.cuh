@@ -25,12 +25,15 @@ namespace stab {
 
 constexpr int LU_NB = 32;
 constexpr int LU_TRSM_THREADS = 128;
+constexpr int LU_PERM = 3 * LU_NB + 1;  // src[32] | nd | dpos[32] | dsrc[32]
+constexpr int LU_SWAP_WARPS = 8;
 
 struct LuBatch {
   cplx* C; size_t cstride; int n;       // C0, n x n, ld n
   cplx* B; size_t bstride; int ldb;     // right-hand side: rows 0..n-1 of an ldb x nrhs block
   int nrhs;
   int* ipiv;                            // n per matrix (absolute row positions, ZGETRF convention, 0-based)
+  int* perm;                            // LU_PERM ints per matrix: the current panel's interchanges as one gather (k_lu_panel)
   int* info;                            // per matrix: 0 or (index of the first exactly-zero pivot) + 1
 };
 
@@ -78,8 +81,66 @@ __global__ void __launch_bounds__(512) k_lu_panel(LuBatch lb, int j0) {
     }
     cta_sync();
   }
+  // The panel's interchanges (ZLASWP, applied in order) composed into ONE gather for the columns outside the panel:
+  // position j0+s receives the entry of row src[s]; the rows outside the top block that were displaced receive dsrc -> dpos.
+  if (c.tid == 0) {
+    int top[LU_NB], dpos[LU_NB], dval[LU_NB], nd = 0;
+    const int r0 = j0 + jb;
+    for (int s = 0; s < LU_NB; ++s) top[s] = j0 + s;
+    for (int s = 0; s < jb; ++s) {
+      const int pr = ipiv[j0 + s];
+      if (pr == j0 + s) continue;
+      if (pr < r0) { const int t = top[s]; top[s] = top[pr - j0]; top[pr - j0] = t; }
+      else {
+        int q = 0;
+        while (q < nd && dpos[q] != pr) ++q;
+        if (q == nd) { dpos[nd] = pr; dval[nd] = pr; ++nd; }
+        const int t = top[s]; top[s] = dval[q]; dval[q] = t;
+      }
+    }
+    int* pm = lb.perm + (size_t)p * LU_PERM;
+    for (int s = 0; s < LU_NB; ++s) { pm[s] = top[s]; pm[LU_NB + 1 + s] = s < nd ? dpos[s] : 0; pm[2 * LU_NB + 1 + s] = s < nd ? dval[s] : 0; }
+    pm[LU_NB] = nd;
+  }
 }
 
+// One WARP per trailing / right-hand-side column (lane = row of the block row): gather the interchanged rows (all loads
+// of a column in flight at once), write the displaced rows back, then the unit-lower solve U12 = L11^-1 (P A12) as a
+// column-oriented forward substitution over lanes (row k broadcast by shuffle, lane l > k eliminates with L11(l,k), which
+// it keeps in registers).  grid (column groups, matrices), LU_SWAP_WARPS warps per CTA.
+__global__ void __launch_bounds__(LU_SWAP_WARPS * 32) k_lu_swap_trsm_warp(LuBatch lb, int j0, int cols_per_cta) {
+  __shared__ cplx sL[LU_NB][LU_NB + 1];
+  __shared__ int spm[LU_PERM];
+  const int p = blockIdx.y, n = lb.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int jb = min(LU_NB, n - j0), r0 = j0 + jb, ntrail = n - r0, ncols = ntrail + lb.nrhs;
+  cplx* C = lb.C + (size_t)p * lb.cstride;
+  for (int e = tid; e < LU_NB * LU_NB; e += LU_SWAP_WARPS * 32) {
+    const int i = e % LU_NB, k = e / LU_NB;
+    sL[i][k] = (i < jb && k < i) ? C[(j0 + i) + (size_t)(j0 + k) * n] : mk(0.0, 0.0);
+  }
+  for (int e = tid; e < LU_PERM; e += LU_SWAP_WARPS * 32) spm[e] = lb.perm[(size_t)p * LU_PERM + e];
+  __syncthreads();
+  cplx Lrow[LU_NB];
+#pragma unroll
+  for (int k = 0; k < LU_NB; ++k) Lrow[k] = sL[lane][k];
+  const int src = spm[lane], nd = spm[LU_NB], dpos = spm[LU_NB + 1 + lane], dsrc = spm[2 * LU_NB + 1 + lane];
+  const int q0 = blockIdx.x * cols_per_cta, q1 = min(ncols, q0 + cols_per_cta);
+  for (int q = q0 + wid; q < q1; q += LU_SWAP_WARPS) {
+    cplx* col = (q < ntrail) ? C + (size_t)(r0 + q) * n : lb.B + (size_t)p * lb.bstride + (size_t)(q - ntrail) * lb.ldb;
+    cplx v = (lane < jb) ? col[src] : mk(0.0, 0.0);
+    cplx d = (lane < nd) ? col[dsrc] : mk(0.0, 0.0);
+    __syncwarp();
+    if (lane < nd) col[dpos] = d;
+#pragma unroll
+    for (int k = 0; k < LU_NB - 1; ++k) {
+      const cplx uk = mk(__shfl_sync(0xffffffffu, v.re, k), __shfl_sync(0xffffffffu, v.im, k));
+      if (lane > k) fms_acc(v, Lrow[k], uk);
+    }
+    if (lane < jb) col[j0 + lane] = v;
+  }
+}
+
+// (v1 of the same step, one thread per column; kept for comparison)
 // column q of the work: q < ntrail -> C0 column j0+jb+q, else right-hand-side column q - ntrail
 __global__ void __launch_bounds__(LU_TRSM_THREADS) k_lu_swap_trsm(LuBatch lb, int j0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

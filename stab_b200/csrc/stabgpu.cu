@@ -109,7 +109,7 @@ struct stabgpu_plan {
   DBuf<cplx> hbY, hbT, hbYp, hbW, hbVx;   // blocked Hessenberg workspaces (Vx: the panel's V with explicit ones / zeros)
   int hbP = 0;
   DBuf<double> scale, hnorm;
-  DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr, vbad;
+  DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr, vbad, lu_perm;
   cudaEvent_t ev[ST_N + 1] = {};
   float ms[ST_N] = {};
   long long launches = 0;
@@ -150,7 +150,7 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
   if (pl->s1.alloc(cap) || pl->s2.alloc(cap) || pl->Re.alloc(cap) || pl->Ma.alloc(cap)) return 1;
   if (pl->kind != 3 && pl->coef.alloc((size_t)cap * ny * (pl->kind == 1 ? 75 : 150))) return 1;
   if (pl->A.alloc((size_t)cap * N * N)) return 1;
-  if (pl->kind == 2 && pl->C.alloc((size_t)cap * n * n)) return 1;
+  if (pl->kind == 2 && (pl->C.alloc((size_t)cap * n * n) || pl->lu_perm.alloc((size_t)cap * LU_PERM))) return 1;
   if (pl->want_vectors && (pl->Hq.alloc((size_t)cap * N * N) || pl->V.alloc((size_t)cap * N * N))) return 1;
   if (pl->tau.alloc((size_t)cap * N) || pl->w.alloc((size_t)cap * N) || pl->eig.alloc((size_t)cap * N) || pl->lam.alloc((size_t)cap * N)) return 1;
   if (pl->scale.alloc((size_t)cap * N) || pl->hnorm.alloc(cap) || pl->cnt.alloc((size_t)cap * N)) return 1;
@@ -462,7 +462,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
 int run_lu_blocked(stabgpu_plan* pl) {
   const int n = pl->n, N = pl->N, np = pl->npts;
   cudaStream_t s = pl->stream;
-  LuBatch lb{pl->C.p, (size_t)n * n, n, pl->A.p, (size_t)N * N, N, N, pl->cnt.p, pl->info_lu.p};
+  LuBatch lb{pl->C.p, (size_t)n * n, n, pl->A.p, (size_t)N * N, N, N, pl->cnt.p, pl->lu_perm.p, pl->info_lu.p};   // ipiv lives in the balancing stage's counter array
   CU(cudaMemsetAsync(pl->info_lu.p, 0, sizeof(int) * np, s));
   const size_t sm_trsm = sizeof(cplx) * (LU_NB * LU_TRSM_THREADS + LU_NB * LU_NB) + sizeof(int) * LU_NB;
   const size_t sm_gemm = PipeCfg<64, 32>::smem_bytes;
@@ -474,7 +474,11 @@ int run_lu_blocked(stabgpu_plan* pl) {
   for (int j0 = 0; j0 < n; j0 += LU_NB) {
     const int jb = (n - j0 < LU_NB) ? n - j0 : LU_NB, r0 = j0 + jb, ncols = (n - r0) + N;
     k_lu_panel<<<np, 512, 0, s>>>(lb, j0);
-    k_lu_swap_trsm<<<dim3((ncols + LU_TRSM_THREADS - 1) / LU_TRSM_THREADS, np), LU_TRSM_THREADS, sm_trsm, s>>>(lb, j0);
+    {
+      int cpc = 64;                                              // columns per CTA: enough CTAs to fill the GPU, few enough to amortise the L11 load
+      while (cpc > LU_SWAP_WARPS && (long long)((ncols + cpc - 1) / cpc) * np < 4LL * g_sm_count) cpc >>= 1;
+      k_lu_swap_trsm_warp<<<dim3((ncols + cpc - 1) / cpc, np), LU_SWAP_WARPS * 32, 0, s>>>(lb, j0, cpc);
+    }
     pl->launches += 2;
     if (r0 < n) {
       const int ti = (n - r0 + 63) / 64, tj = (N + 31) / 32;
