@@ -124,7 +124,7 @@ def run_reference(args):
                          "lapack": "scipy OpenBLAS zgesv+zgeev('N','%s'), %s workspace" % ("V" if want_vectors else "N", "lwork=2n (as coded)" if as_coded else "optimal")},
         "e2e": {"value": val, "unit": "eigensolves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_dict(args, npts):
@@ -195,8 +195,23 @@ def fp64_gemm_peak(torch, dev):
     return best
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL's version banner, library
+    chatter written to fd 1 from C) was redirected to stderr by main()."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -388,7 +403,7 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": "eigensolves/s", "cores": used, "kind": "port",
                                 "sample": f"{sample} points of the same sweep, one worker per core, 1 BLAS thread each, "
                                           f"{'lwork=2n' if as_coded else 'optimal workspace'} (faster of the two), {dt:.1f} s"}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
