@@ -6,8 +6,9 @@
 // Per panel:
 //   k_lu_panel      one CTA per matrix: ZGETF2 on the n-j0 x 32 panel (IZAMAX pivot = first maximum of |re|+|im|,
 //                   reciprocal scaling, rank-1 updates inside the panel); the pivot rows are interchanged inside the panel only
-//   k_lu_swap_trsm  one thread per trailing / right-hand-side column: the panel's row interchanges (ZLASWP) and the
-//                   unit-lower 32 x 32 triangular solve that turns the pivot rows into the U12 block row (ZTRSM 'L','L','N','U')
+//   k_lu_swap_trsm_warp  one warp per trailing / right-hand-side column: the panel's row interchanges (ZLASWP), composed
+//                   into one gather by k_lu_panel, and the unit-lower 32 x 32 triangular solve that turns the pivot rows
+//                   into the U12 block row (ZTRSM 'L','L','N','U')
 //   k_lu_gemm<0>    DMMA rank-32 update  [C22 | B2] -= L21 [U12 | B1]   (gemm_pipe.cuh, persistent cp.async ring)
 // Back substitution, last block row first:
 //   k_lu_back_trsm  X_R = U_RR^-1 Y_R (one thread per right-hand-side column, true complex divisions as ZTRSM)
@@ -140,41 +141,6 @@ __global__ void __launch_bounds__(LU_SWAP_WARPS * 32) k_lu_swap_trsm_warp(LuBatc
   }
 }
 
-// (v1 of the same step, one thread per column; kept for comparison)
-// column q of the work: q < ntrail -> C0 column j0+jb+q, else right-hand-side column q - ntrail
-__global__ void __launch_bounds__(LU_TRSM_THREADS) k_lu_swap_trsm(LuBatch lb, int j0) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* sU = reinterpret_cast<cplx*>(smem_raw);                       // [LU_NB][LU_TRSM_THREADS]
-  cplx* sL = sU + LU_NB * LU_TRSM_THREADS;                            // [LU_NB][LU_NB] unit lower block, row-major
-  int* sp = reinterpret_cast<int*>(sL + LU_NB * LU_NB);               // [LU_NB]
-  const int p = blockIdx.y, n = lb.n, tid = threadIdx.x;
-  const int jb = min(LU_NB, n - j0), r0 = j0 + jb, ntrail = n - r0;
-  cplx* C = lb.C + (size_t)p * lb.cstride;
-  for (int e = tid; e < jb * jb; e += LU_TRSM_THREADS) {
-    const int i = e % jb, k = e / jb;
-    sL[i * LU_NB + k] = C[(j0 + i) + (size_t)(j0 + k) * n];
-  }
-  if (tid < jb) sp[tid] = lb.ipiv[(size_t)p * n + j0 + tid];
-  __syncthreads();
-  const int q = blockIdx.x * LU_TRSM_THREADS + tid;
-  if (q >= ntrail + lb.nrhs) return;
-  cplx* col = (q < ntrail) ? C + (size_t)(r0 + q) * n : lb.B + (size_t)p * lb.bstride + (size_t)(q - ntrail) * lb.ldb;
-#define LU_U(s) sU[(s) * LU_TRSM_THREADS + tid]
-  for (int s = 0; s < jb; ++s) LU_U(s) = col[j0 + s];
-  for (int s = 0; s < jb; ++s) {                                      // ZLASWP, in order
-    const int pr = sp[s];
-    if (pr == j0 + s) continue;
-    if (pr < r0) { const cplx t = LU_U(s); LU_U(s) = LU_U(pr - j0); LU_U(pr - j0) = t; }
-    else { const cplx t = col[pr]; col[pr] = LU_U(s); LU_U(s) = t; }
-  }
-  for (int i = 1; i < jb; ++i) {                                      // unit lower triangular solve
-    cplx acc = LU_U(i);
-    for (int k = 0; k < i; ++k) fms_acc(acc, sL[i * LU_NB + k], LU_U(k));
-    LU_U(i) = acc;
-  }
-  for (int s = 0; s < jb; ++s) col[j0 + s] = LU_U(s);
-}
-
 // X_R = U_RR^-1 Y_R for the block row R = [i0, i0 + bs), one thread per right-hand-side column
 __global__ void __launch_bounds__(LU_TRSM_THREADS) k_lu_back_trsm(LuBatch lb, int i0, int bs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -190,6 +156,7 @@ __global__ void __launch_bounds__(LU_TRSM_THREADS) k_lu_back_trsm(LuBatch lb, in
   const int q = blockIdx.x * LU_TRSM_THREADS + tid;
   if (q >= lb.nrhs) return;
   cplx* col = lb.B + (size_t)p * lb.bstride + (size_t)q * lb.ldb;
+#define LU_U(s) sU[(s) * LU_TRSM_THREADS + tid]
   for (int s = 0; s < bs; ++s) LU_U(s) = col[i0 + s];
   for (int i = bs - 1; i >= 0; --i) {
     const cplx x = cdiv(LU_U(i), sT[i + i * LU_NB]);

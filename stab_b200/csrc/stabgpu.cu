@@ -464,9 +464,8 @@ int run_lu_blocked(stabgpu_plan* pl) {
   cudaStream_t s = pl->stream;
   LuBatch lb{pl->C.p, (size_t)n * n, n, pl->A.p, (size_t)N * N, N, N, pl->cnt.p, pl->lu_perm.p, pl->info_lu.p};   // ipiv lives in the balancing stage's counter array
   CU(cudaMemsetAsync(pl->info_lu.p, 0, sizeof(int) * np, s));
-  const size_t sm_trsm = sizeof(cplx) * (LU_NB * LU_TRSM_THREADS + LU_NB * LU_NB) + sizeof(int) * LU_NB;
+  const size_t sm_trsm = sizeof(cplx) * (LU_NB * LU_TRSM_THREADS + LU_NB * LU_NB);
   const size_t sm_gemm = PipeCfg<64, 32>::smem_bytes;
-  CU(cudaFuncSetAttribute(k_lu_swap_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trsm));
   CU(cudaFuncSetAttribute(k_lu_back_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trsm));
   CU(cudaFuncSetAttribute(k_lu_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gemm));
   CU(cudaFuncSetAttribute(k_lu_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gemm));
