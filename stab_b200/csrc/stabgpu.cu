@@ -851,8 +851,16 @@ int stabgpu_spatial_batch(const stabgpu_params* p, const double* vm, const doubl
 
 int stabgpu_zgeev_batch(int n, int batch, const double* A, int want_vectors, double* w, double* V, int* info) {
   if (ensure_init()) return 1;
-  if (n < 2 || batch < 1 || !A || !w) return fail("libstabgpu: bad argument");
+  if (n < 1 || batch < 1 || !A || !w) return fail("libstabgpu: bad argument");
   if (want_vectors && !V) return fail("libstabgpu: want_vectors set but V is NULL");
+  if (n == 1) {                                        // ZGEEV's quick return: the entry is the eigenvalue, the vector is 1
+    for (int b = 0; b < batch; ++b) {
+      w[2 * b] = A[2 * b]; w[2 * b + 1] = A[2 * b + 1];
+      if (want_vectors) { V[2 * b] = 1.0; V[2 * b + 1] = 0.0; }
+      if (info) info[b] = 0;
+    }
+    return 0;
+  }
   stabgpu_plan* pl = new stabgpu_plan();
   pl->kind = 3; pl->ny = 0; pl->n = n; pl->N = n; pl->want_vectors = want_vectors ? 1 : 0;
   int rc = plan_alloc(pl, batch);

@@ -112,6 +112,21 @@ def test_zgeev_batch_random(n, batch):
         assert d.max() < 1e-11 * np.abs(w[b]).max()
 
 
+@pytest.mark.parametrize("n,batch", [(1, 3), (2, 3), (3, 2), (5, 1), (31, 2), (33, 2), (65, 3), (129, 2), (257, 1), (513, 1), (639, 1), (16, 700)])
+def test_zgeev_batch_ragged_orders(n, batch):
+    """Orders around every tile / warp / panel boundary (32, 64, 128, 256, 512, 640), the trivial orders, and a batch larger
+    than one wave of CTAs: eigenvalues against numpy, residuals at rounding level."""
+    A = _rand(n, 900 + n, batch)
+    w, V, info = sb.zgeev_batch(A, want_vectors=True)
+    assert np.all(info == 0)
+    for b in range(min(batch, 8)):
+        ref = np.linalg.eigvals(A[b])
+        _, d = match_spectra(ref, w[b])
+        assert d.max() < 1e-11 * np.abs(ref).max()
+        assert eigpair_residuals(A[b], w[b], V[b]).max() < max(1e-13, 4 * n * np.finfo(float).eps)
+        assert np.abs(np.linalg.norm(V[b], axis=0) - 1).max() < 1e-12
+
+
 def test_eigenvector_paths_agree():
     """Register-resident inverse iteration + tensor-core back-transformation (default) against the v1
     warp kernel (per-vector reflector application): same vectors to rounding."""
