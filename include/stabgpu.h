@@ -51,7 +51,8 @@ int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb)
 /* tuning knobs of the QR stage (window size, shifts per sweep, threads); 0 keeps the default */
 int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads);
 /* Hessenberg stage variant: 1 (default) batched blocked reduction with DMMA tensor-core updates; 2 the same with a
- * scalar-FMA GEMM (validation of the tensor-core path); 0 the unblocked one-CTA-per-matrix kernel of v1 */
+ * scalar-FMA GEMM (validation of the tensor-core path); 0 the unblocked one-CTA-per-matrix kernel of v1; 5 as 1 with the right and
+ * left trailing updates fused into one rank-64 pass (measured slower, kept as a validated variant) */
 int stabgpu_set_hess_mode(int mode);
 /* eigenvector stage variant: 1 (default) register-resident inverse iteration + tensor-core back-transformation; 0 the v1 warp kernel */
 int stabgpu_set_evec_mode(int mode);

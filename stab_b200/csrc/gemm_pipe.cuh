@@ -26,6 +26,9 @@ struct GemmProb {
   const cplx* R; long long rsl, rsj;   // R(l,j) = R[l*rsl + j*rsj]
   cplx* C; int ldc;
   int m, nc, K;                        // m <= 0 or nc <= 0 or K <= 0: nothing to do
+  // optional second operand pair with the same strides: C -= L R + L2 R2 in ONE pass over C (the K-chunks of the
+  // second pair follow those of the first in the work list)
+  const cplx* L2 = nullptr; const cplx* R2 = nullptr; int K2 = 0;
 };
 
 template <int TM, int TN>
@@ -65,7 +68,7 @@ SD_DEV void gemm_pipe_run(const ProbF& probf, int tiles_i, int tiles_j, int nmat
   const bool bneg = (CONJL ? (((g & 1) == 1) && (qsel == 0)) : (((g & 1) == 0) && (qsel == 1))) != SUB;
   const bool aneg = CONJR && (qsel == 1);
 
-  struct Item { int t, chunk, nchunks, i0, j0; GemmProb p; bool valid; };
+  struct Item { int t, chunk, nchunks, nch1, i0, j0; GemmProb p; bool valid; };
   const int total = tiles_i * tiles_j * nmat;
   auto load_tile = [&](Item& it) {                             // advance it.t to the next tile with work
     it.valid = false;
@@ -75,7 +78,8 @@ SD_DEV void gemm_pipe_run(const ProbF& probf, int tiles_i, int tiles_j, int nmat
       it.p = probf(mat);
       it.i0 = ti * TM; it.j0 = tj * TN;
       if (it.p.m > 0 && it.p.nc > 0 && it.p.K > 0 && it.i0 < it.p.m && it.j0 < it.p.nc) {
-        it.nchunks = (it.p.K + GEMM_KC - 1) / GEMM_KC; it.chunk = 0; it.valid = true;
+        it.nch1 = (it.p.K + GEMM_KC - 1) / GEMM_KC;
+        it.nchunks = it.nch1 + ((it.p.L2 && it.p.K2 > 0) ? (it.p.K2 + GEMM_KC - 1) / GEMM_KC : 0); it.chunk = 0; it.valid = true;
         return;
       }
       it.t += gridDim.x;
@@ -92,20 +96,24 @@ SD_DEV void gemm_pipe_run(const ProbF& probf, int tiles_i, int tiles_j, int nmat
   auto issue_one = [&](const Item& it, int stage, int u) {
     double* sL = smem + stage * G::STAGE;
     double* sR = sL + GEMM_KC * G::SLD;
-    const int k0 = it.chunk * GEMM_KC;
+    const bool second = it.chunk >= it.nch1;
+    const int k0 = (second ? it.chunk - it.nch1 : it.chunk) * GEMM_KC;
+    const int Kc = second ? it.p.K2 : it.p.K;
+    const cplx* Lb = second ? it.p.L2 : it.p.L;
+    const cplx* Rb = second ? it.p.R2 : it.p.R;
     if (u < NLD) {
       const int idx = tid + u * GEMM_THREADS;
       int i, l;
       if (LKFAST) { l = (idx & 3) + 4 * (idx / (4 * TM)); i = (idx >> 2) % TM; } else { i = idx % TM; l = idx / TM; }
-      const bool ok = (it.i0 + i < it.p.m) && (k0 + l < it.p.K);
-      const cplx* src = ok ? it.p.L + (long long)(it.i0 + i) * it.p.lsi + (long long)(k0 + l) * it.p.lsl : it.p.L;
+      const bool ok = (it.i0 + i < it.p.m) && (k0 + l < Kc);
+      const cplx* src = ok ? Lb + (long long)(it.i0 + i) * it.p.lsi + (long long)(k0 + l) * it.p.lsl : Lb;
       cp_async16_zfill(sL + l * G::SLD + 2 * i, src, ok);
     } else {
       const int idx = tid + (u - NLD) * GEMM_THREADS;
       int j, l;
       if (RKFAST) { l = (idx & 3) + 4 * (idx / (4 * TN)); j = (idx >> 2) % TN; } else { j = idx % TN; l = idx / TN; }
-      const bool ok = (it.j0 + j < it.p.nc) && (k0 + l < it.p.K);
-      const cplx* src = ok ? it.p.R + (long long)(k0 + l) * it.p.rsl + (long long)(it.j0 + j) * it.p.rsj : it.p.R;
+      const bool ok = (it.j0 + j < it.p.nc) && (k0 + l < Kc);
+      const cplx* src = ok ? Rb + (long long)(k0 + l) * it.p.rsl + (long long)(it.j0 + j) * it.p.rsj : Rb;
       cp_async16_zfill(sR + l * G::SRD + 2 * j, src, ok);
     }
   };

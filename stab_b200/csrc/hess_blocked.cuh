@@ -35,6 +35,8 @@ struct HessBatch {
   int P;
   int mat0;             // first matrix of this launch group (the batch is split over two streams)
   cplx* Vx;             // n x NB per matrix: the current panel's V with explicit ones / zeros (pipelined GEMM path)
+  cplx* S = nullptr;    // NB x NB per matrix: V^H Y of the current panel (fused trailing update)
+  cplx* Vh = nullptr;   // NB x n per matrix: conj(V(k+NB+j, :)) as a plain NB x nc operand (fused trailing update)
 };
 
 SD_DEV cplx hb_v(const cplx* A, int lda, int k, int ihi, int r, int l) {   // V(r, l) of the panel starting at k
@@ -320,6 +322,37 @@ SD_DEV void cta_hb_w_T(const Cta& c, const cplx* T, cplx* W, int ncols, int colb
       for (int m = l; m < HB_NB; ++m) fma_acc(s, T[l + m * HB_NB], w[m]);
       W[l + (size_t)j * HB_NB] = s;
     }
+  }
+}
+
+// Fused trailing update (hess_mode 5): column j of the trailing block (global column c = k + NB + j).
+//   w0 = V^H A_old(:, c)   (from the W-product on the NOT yet right-updated matrix)
+//   W(:, j)  = T^H ( w0 - S conj(V(c, :))^T ),   S = V^H Y      -- equals T^H V^H (A_old - Y V^H)(:, c)
+//   Vh(:, j) = conj(V(c, :))^T                                  -- the right update's operand as a plain NB x nc matrix
+SD_DEV void cta_hb_w_T_fused(const Cta& c, const HessBatch& hb, int mat, int panel, int colblock, const cplx* sS, const cplx* sT) {
+  const int n = hb.n;
+  const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
+  const int k = ilo + panel * HB_NB;
+  const int ncols = n - (k + HB_NB);
+  const int j = colblock * c.nt + c.tid;
+  if (j >= ncols) return;
+  const cplx* A = hb.A + (size_t)mat * hb.astride;
+  cplx* W = hb.W + (size_t)mat * n * HB_NB;
+  cplx* Vh = hb.Vh + (size_t)mat * n * HB_NB;
+  const int col = k + HB_NB + j;
+  cplx w[HB_NB], v[HB_NB];
+  for (int l = 0; l < HB_NB; ++l) { w[l] = W[l + (size_t)j * HB_NB]; v[l] = conj(hb_v(A, n, k, ihi, col, l)); }
+  for (int l = 0; l < HB_NB; ++l) Vh[l + (size_t)j * HB_NB] = v[l];
+  if (col <= ihi)
+    for (int i = 0; i < HB_NB; ++i) {
+      cplx s = w[i];
+      for (int l = 0; l < HB_NB; ++l) fms_acc(s, sS[i + l * HB_NB], v[l]);
+      w[i] = s;
+    }
+  for (int l = HB_NB - 1; l >= 0; --l) {        // (T^H w)[l] = sum_{m<=l} conj(T[m,l]) w[m]
+    cplx s = mk(0.0, 0.0);
+    for (int m = 0; m <= l; ++m) fma_acc_conj(s, sT[m + l * HB_NB], w[m]);
+    W[l + (size_t)j * HB_NB] = s;
   }
 }
 

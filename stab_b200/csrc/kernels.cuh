@@ -262,7 +262,7 @@ __global__ void k_hb_vx(HessBatch hb, int panel) {
   for (int l = 0; l < HB_NB; ++l) Vx[r + (size_t)l * n] = hb_v(A, n, k, ihi, r, l);
 }
 
-enum PipePhase { PP_YTOP = 0, PP_RIGHT_TRAIL, PP_RIGHT_PANEL, PP_LEFT_W, PP_LEFT_UPD, PP_BT_W, PP_BT_UPD };
+enum PipePhase { PP_YTOP = 0, PP_RIGHT_TRAIL, PP_RIGHT_PANEL, PP_LEFT_W, PP_LEFT_UPD, PP_BT_W, PP_BT_UPD, PP_RIGHT_TOP, PP_S, PP_FUSED_UPD };
 
 template <int PHASE>
 struct HbProb {
@@ -303,6 +303,22 @@ struct HbProb {
       q.L = Vx + (k + 1); q.lsi = 1; q.lsl = n;
       q.R = W; q.rsl = 1; q.rsj = HB_NB;
       q.C = A + (k + 1) + (size_t)(k + HB_NB) * lda; q.ldc = lda;
+    } else if (PHASE == PP_RIGHT_TOP) {     // A(0:k+1, k+NB:ihi+1) -= Y(0:k+1, :) V(k+NB:ihi+1, :)^H   (rows above the panel only)
+      q.m = k + 1; q.nc = ihi + 1 - (k + HB_NB); q.K = HB_NB;
+      q.L = Y; q.lsi = 1; q.lsl = n;
+      q.R = Vx + (k + HB_NB); q.rsl = n; q.rsj = 1;
+      q.C = A + (size_t)(k + HB_NB) * lda; q.ldc = lda;
+    } else if (PHASE == PP_S) {             // S (NB x NB) = V^H Y(k+1:ihi+1, :)
+      q.m = HB_NB; q.nc = HB_NB; q.K = ihi - k;
+      q.L = Vx + (k + 1); q.lsi = n; q.lsl = 1;
+      q.R = Y + (k + 1); q.rsl = 1; q.rsj = n;
+      q.C = hb.S + (size_t)mat * HB_NB * HB_NB; q.ldc = HB_NB;
+    } else if (PHASE == PP_FUSED_UPD) {     // A(k+1:ihi+1, k+NB:n) -= Y Vh + V W   (right and left update in one pass)
+      q.m = ihi - k; q.nc = n - (k + HB_NB); q.K = HB_NB;
+      q.L = Y + (k + 1); q.lsi = 1; q.lsl = n;
+      q.R = hb.Vh + (size_t)mat * n * HB_NB; q.rsl = 1; q.rsj = HB_NB;
+      q.L2 = Vx + (k + 1); q.R2 = W; q.K2 = HB_NB;
+      q.C = A + (k + 1) + (size_t)(k + HB_NB) * lda; q.ldc = lda;
     } else if (PHASE == PP_BT_W) {          // W (NB x n) = V^H X(k+1:ihi+1, :)
       cplx* Xm = X + (size_t)mat * xstride;
       q.m = HB_NB; q.nc = n; q.K = ihi - k;
@@ -327,8 +343,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_pipe(HessBatch hb, cpl
   HbProb<PHASE> pf{hb, X, xstride, panel};
   //                                    TM  TN  SUB    CONJL  CONJR  LKFAST RKFAST
   if (PHASE == PP_YTOP)                                   gemm_pipe_run<64, 32, false, false, false, false, true>(pf, tiles_i, tiles_j, nmat, smem);
-  else if (PHASE == PP_RIGHT_TRAIL || PHASE == PP_RIGHT_PANEL) gemm_pipe_run<64, 32, true, false, true, false, false>(pf, tiles_i, tiles_j, nmat, smem);
-  else if (PHASE == PP_LEFT_W || PHASE == PP_BT_W)        gemm_pipe_run<32, 64, false, true, false, true, true>(pf, tiles_i, tiles_j, nmat, smem);
+  else if (PHASE == PP_RIGHT_TRAIL || PHASE == PP_RIGHT_PANEL || PHASE == PP_RIGHT_TOP) gemm_pipe_run<64, 32, true, false, true, false, false>(pf, tiles_i, tiles_j, nmat, smem);
+  else if (PHASE == PP_LEFT_W || PHASE == PP_BT_W || PHASE == PP_S) gemm_pipe_run<32, 64, false, true, false, true, true>(pf, tiles_i, tiles_j, nmat, smem);
   else                                                    gemm_pipe_run<64, 32, true, false, false, false, true>(pf, tiles_i, tiles_j, nmat, smem);
 }
 #endif
@@ -345,6 +361,21 @@ __global__ void k_hb_w_T(HessBatch hb, int panel) {
   const int k = ilo + panel * HB_NB;
   if (k >= ihi) return;
   cta_hb_w_T(c, hb.T + ((size_t)mat * hb.P + panel) * HB_NB * HB_NB, hb.W + (size_t)mat * n * HB_NB, n - (k + HB_NB), blockIdx.x, true);
+}
+
+__global__ void k_hb_w_T_fused(HessBatch hb, int panel) {
+  __shared__ cplx sS[HB_NB * HB_NB], sT[HB_NB * HB_NB];
+  Cta c = make_cta(nullptr);
+  const int mat = hb.mat0 + blockIdx.y;
+  const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
+  const int k = ilo + panel * HB_NB;
+  if (k >= ihi) return;
+  for (int e = c.tid; e < HB_NB * HB_NB; e += c.nt) {
+    sS[e] = hb.S[(size_t)mat * HB_NB * HB_NB + e];
+    sT[e] = hb.T[((size_t)mat * hb.P + panel) * HB_NB * HB_NB + e];
+  }
+  cta_sync();
+  cta_hb_w_T_fused(c, hb, mat, panel, blockIdx.x, sS, sT);
 }
 
 // ---- stage 3c: prepare the QR operand: Hq := upper Hessenberg part of A (zeros below), plus the

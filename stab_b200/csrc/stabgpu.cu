@@ -106,7 +106,7 @@ struct stabgpu_plan {
   bool has_Re = false, has_Ma = false;
   // work
   DBuf<cplx> coef, A, C, Hq, V, tau, w, eig, lam;
-  DBuf<cplx> hbY, hbT, hbYp, hbW, hbVx;   // blocked Hessenberg workspaces (Vx: the panel's V with explicit ones / zeros)
+  DBuf<cplx> hbY, hbT, hbYp, hbW, hbVx, hbS, hbVh;   // blocked Hessenberg workspaces (Vx: the panel's V with explicit ones / zeros)
   int hbP = 0;
   DBuf<double> scale, hnorm;
   DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr, vbad, lu_perm;
@@ -131,7 +131,7 @@ size_t per_point_bytes(int kind, int n, int N, int ny, int want_vectors) {
   if (want_vectors) b += 2 * (size_t)N * N * 16;     // Hq + V
   b += (size_t)ny * 150 * 16;                        // coefficients
   b += (size_t)N * (16 * 4 + 8 + 4 * 3) + 64;
-  b += (size_t)N * 16 * (4 * HB_NB + HB_CHUNKS) + 16 * HB_NB * HB_NB;   // blocked Hessenberg: Y, W, Vx, T, Ypart
+  b += (size_t)N * 16 * (5 * HB_NB + HB_CHUNKS) + 2 * 16 * HB_NB * HB_NB;   // blocked Hessenberg: Y, W, Vx, Vh, T, S, Ypart
   return b;
 }
 
@@ -157,7 +157,8 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
   if (pl->blkend.alloc((size_t)cap * N) || pl->kr.alloc((size_t)cap * N) || pl->vbad.alloc((size_t)cap * N)) return 1;
   pl->hbP = (N - 1 + HB_NB - 1) / HB_NB;
   if (pl->hbY.alloc((size_t)cap * N * HB_NB) || pl->hbT.alloc((size_t)cap * pl->hbP * HB_NB * HB_NB) ||
-      pl->hbYp.alloc((size_t)cap * N * HB_CHUNKS) || pl->hbW.alloc((size_t)cap * N * HB_NB) || pl->hbVx.alloc((size_t)cap * N * HB_NB)) return 1;
+      pl->hbYp.alloc((size_t)cap * N * HB_CHUNKS) || pl->hbW.alloc((size_t)cap * N * HB_NB) || pl->hbVx.alloc((size_t)cap * N * HB_NB) ||
+      pl->hbS.alloc((size_t)cap * HB_NB * HB_NB) || pl->hbVh.alloc((size_t)cap * N * HB_NB)) return 1;
   if (pl->ilohi.alloc(2 * (size_t)cap) || pl->info_lu.alloc(cap) || pl->info_qr.alloc(cap) || pl->info_v.alloc(cap)) return 1;
   CU(cudaStreamCreate(&pl->stream));
   CU(cudaStreamCreate(&pl->stream2));
@@ -244,6 +245,24 @@ int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, 
     return 0;
   }
   const int tm = (N + 63) / 64;
+  if (g_tune.hess_mode == 5) {               // as mode 1, with the right and left trailing updates fused into one rank-64 pass
+    if (launch_vx(pl, hb, nmat, s, p)) return 1;
+    if (launch_pipe<PP_YTOP>(pl, hb, nullptr, 0, nmat, s, p, tm, 1)) return 1;
+    k_hb_ytop_T<<<dim3((N + 127) / 128, nmat), 128, 0, s>>>(hb, p);
+    pl->launches += 1;
+    if (trail_max > 0) {
+      if (launch_pipe<PP_S>(pl, hb, nullptr, 0, nmat, s, p, 1, 1)) return 1;
+      if (launch_pipe<PP_LEFT_W>(pl, hb, nullptr, 0, nmat, s, p, 1, (trail_max + 63) / 64)) return 1;     // on the matrix BEFORE the right update
+      k_hb_w_T_fused<<<dim3((trail_max + 127) / 128, nmat), 128, 0, s>>>(hb, p);
+      pl->launches += 1;
+      if (launch_pipe<PP_RIGHT_TOP>(pl, hb, nullptr, 0, nmat, s, p, tm, (trail_max + 31) / 32)) return 1;
+    }
+    if (launch_pipe<PP_RIGHT_PANEL>(pl, hb, nullptr, 0, nmat, s, p, tm, 1)) return 1;
+    if (trail_max > 0 && launch_pipe<PP_FUSED_UPD>(pl, hb, nullptr, 0, nmat, s, p, (rows_max + 63) / 64, (trail_max + 31) / 32)) return 1;
+    if (hmark(pl, s, 2)) return 1;
+    CU(cudaGetLastError());
+    return 0;
+  }
   if (g_tune.hess_mode == 1) {               // pipelined path: plain operands (V materialised), persistent cp.async ring
     if (launch_vx(pl, hb, nmat, s, p)) return 1;
     if (launch_pipe<PP_YTOP>(pl, hb, nullptr, 0, nmat, s, p, tm, 1)) return 1;
@@ -297,7 +316,7 @@ int run_hessenberg(stabgpu_plan* pl) {
     return 0;
   }
   const bool mma = g_tune.hess_mode == 1 || g_tune.hess_mode == 3;   // 1: pipelined DMMA kernels, 3: the tile-per-CTA DMMA kernels
-  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p};
+  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p, pl->hbS.p, pl->hbVh.p};
   pl->pev_n = 0;
   if (hmark(pl, s, 3)) return 1;
   const int half = (g_tune.hess_streams >= 2 && np >= 16) ? (np + 1) / 2 : np;
@@ -418,7 +437,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
       for (int p = pl->hbP - 1; p >= 0; --p) {
         const int rows_max = N - 1 - p * HB_NB;
         if (rows_max <= 0) continue;
-        if (g_tune.hess_mode == 1) {
+        if (g_tune.hess_mode == 1 || g_tune.hess_mode == 5) {
           if (launch_vx(pl, hb, cnt, s, p)) return 1;
           if (launch_pipe<PP_BT_W>(pl, hb, pl->V.p, st, cnt, s, p, 1, tn)) return 1;
           k_bt_w_T<<<dim3((N + 127) / 128, cnt), 128, 0, s>>>(hb, p);

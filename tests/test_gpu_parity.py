@@ -71,7 +71,7 @@ def test_balance_bitwise_and_hessenberg_similarity():
         assert np.abs(q @ H @ q.conj().T - ba).max() < 1e-13 * n * np.abs(ba).max()
 
 
-@pytest.mark.parametrize("mode", [1, 2, 0])
+@pytest.mark.parametrize("mode", [1, 5, 2, 0])
 @pytest.mark.parametrize("n", [33, 97, 320, 640])
 def test_hessenberg_matches_zgehrd(n, mode):
     """Stage 3b against LAPACK's ZGEHRD on the same balanced matrix: H, the reflectors and tau agree to
