@@ -386,16 +386,16 @@ __global__ void k_prep_qr(const cplx* A, size_t astride, cplx* Hq, size_t hstrid
   const int p = blockIdx.x;
   const cplx* a = A + (size_t)p * astride;
   cplx* h = Hq + (size_t)p * hstride;
-  double mx = 0.0;
+  double mx = 0.0, bad = 0.0;                           // bad: a NaN somewhere (fmax would drop it)
   for (int r = c.tid; r < n; r += c.nt) {
     double s = 0.0;
     for (int j = (r > 0 ? r - 1 : 0); j < n; ++j) s += cabs(a[r + (size_t)j * n]);
+    if (!(s == s)) bad = 1.0;
     mx = fmax(mx, s);
   }
-  double dummy = 0.0;
-  cta_max2(c, mx, dummy);
+  cta_max2(c, mx, bad);
   if (c.tid == 0) {
-    hnorm[p] = mx;
+    hnorm[p] = (bad != 0.0) ? (mx - mx) / (mx - mx) : mx;   // NaN marks the matrix for the QR and eigenvector stages
     // diagonal blocks of H separated by exactly-zero subdiagonals (ZHSEIN's KL..KR with FROMQR):
     // blkend[i] = last index of the block containing i
     int end = n - 1;
@@ -426,7 +426,7 @@ SD_HD size_t hqr_smem_bytes(const HqrLaunch& q) {
   return b;
 }
 
-__global__ void __launch_bounds__(256, 2) k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q, long long* prof) {
+__global__ void __launch_bounds__(256, 2) k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q, long long* prof, const double* hnorm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* sp = smem_raw;
   double* red = reinterpret_cast<double*>(sp); sp += 160 * sizeof(double);
@@ -444,6 +444,14 @@ __global__ void __launch_bounds__(256, 2) k_hqr(cplx* Hq, size_t hstride, int n,
   sh.prof = (prof && p == 0) ? sprof : nullptr;
   if (sh.prof && threadIdx.x < 16) sprof[threadIdx.x] = 0;
   __syncthreads();
+  // A matrix with a NaN or an infinity (bad sweep value, overflowed operator) never deflates: report it as ZHSEQR's
+  // "failed to converge" at once (info = n) instead of iterating to the limit; the other points of the batch go on.
+  const double hn = hnorm[p];
+  if (!(hn == hn) || hn > 1.0e300) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) w[(size_t)p * n + i] = mk(hn - hn, hn - hn);   // NaN
+    if (threadIdx.x == 0) info[p] = n;
+    return;
+  }
   int r = cta_hqr(c, sh, Hq + (size_t)p * hstride, n, n, ilohi[2 * p], ilohi[2 * p + 1], w + (size_t)p * n);
   if (threadIdx.x == 0) info[p] = r;
   if (sh.prof && threadIdx.x < 16) prof[threadIdx.x] = sprof[threadIdx.x];

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(512) k_lu_panel(LuBatch lb, int j0) {
       if (m > best) { best = m; bi = r; }
     }
     cta_argmax(c, best, bi);
+    if (!(best > 0.0) || bi >= n) { best = 0.0; bi = j; }   // a column of zeros -- or of NaNs, which no comparison selects
     if (c.tid == 0) ipiv[j] = bi;
     if (best == 0.0) {                                   // exactly singular column: ZGETF2 records it and goes on
       if (c.tid == 0 && lb.info[p] == 0) lb.info[p] = j + 1;

@@ -556,7 +556,7 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
       CU(cudaMemsetAsync(g_qrprof_dev, 0, 16 * sizeof(long long), s));
       prof = g_qrprof_dev;
     }
-    k_hqr<<<np, g_tune.qr_threads, sm, s>>>(Hq, st, N, pl->ilohi.p, pl->w.p, pl->info_qr.p, q, prof);
+    k_hqr<<<np, g_tune.qr_threads, sm, s>>>(Hq, st, N, pl->ilohi.p, pl->w.p, pl->info_qr.p, q, prof, pl->hnorm.p);
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(pl->ev[ST_QR + 1], s));

@@ -343,6 +343,29 @@ def test_temporal_ny128_full_size_properties():
         assert abs(omg[k].sum() - np.trace(M)) < 1e-9 * np.abs(omg[k]).sum()
 
 
+def test_bad_point_is_reported_and_does_not_poison_the_batch():
+    """A NaN sweep value (or an Inf matrix entry) fails THAT point with a LAPACK-style info > 0 at once -- no iteration to
+    the limit -- and leaves the other points of the batch bit-identical to a clean call (temporal.f90:806-809 stops on
+    info /= 0; a batched caller needs the per-point status instead)."""
+    import time
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=32)
+    al = np.array([0.2, np.nan, 0.3]) + 0j
+    t0 = time.perf_counter()
+    omg, ev, info = sb.temporal_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], al, al * 0, want_vectors=True)
+    assert time.perf_counter() - t0 < 10.0
+    assert info[0] == 0 and info[2] == 0 and info[1] > 0
+    ref, _, i2 = sb.temporal_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], al[[0, 2]], al[[0, 2]] * 0, want_vectors=False)
+    assert np.array_equal(ref[0], omg[0]) and np.array_equal(ref[1], omg[2]) and not np.isnan(ev[0]).any()
+    p2, g2 = oracle_case("ts_spatial_ny32.inp", "ts_profile.0", ny=24)
+    om = np.array([0.08, np.nan, 0.1]) + 0j
+    alp, _, info = sb.spatial_batch(to_params(p2), g2["vm"], g2["deta"], g2["d2eta"], om, om * 0, h5=g2["h5"])
+    assert info[0] == 0 and info[2] == 0 and info[1] > 0 and not np.isnan(alp[[0, 2]]).any()
+    A = _rand(40, 3, 3)
+    A[1, 3, 4] = np.inf
+    w, V, info = sb.zgeev_batch(A, want_vectors=True)
+    assert info[0] == 0 and info[2] == 0 and info[1] > 0 and not np.isnan(w[[0, 2]]).any()
+
+
 def test_temporal_re_ma_overrides():
     """Per-point Re/Ma overrides (neutral-curve sweeps, config C5) equal separate calls."""
     p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=32)
