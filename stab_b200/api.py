@@ -168,3 +168,45 @@ def mspatial(case: Case, omin, omax, oinc, bmin, bmax, binc, outdir: Optional[st
             _write(case, os.path.join(outdir, makename("eig", lo + k + 1)), 2, complex(o[lo + k]), case.alpha,
                    complex(b[lo + k]), alp[k], None if ev is None else ev[k])
     return dict(omega=o[lo:hi], beta=b[lo:hi], alp=alp, evec=ev, info=info, lo=lo, hi=hi)
+
+
+def read_delta(path: str):
+    """delta.dat of mspatial.f90:31-66: rows `x_body delta`, lines starting with '#' skipped.  Returns (xb, delta)."""
+    xb, delta = [], []
+    with open(path) as fh:
+        for line in fh:
+            if not line.strip() or line.lstrip().startswith("#"):
+                continue
+            t = _tokens(line)
+            xb.append(float(t[0]))
+            delta.append(float(t[1]))
+    return np.array(xb), np.array(delta)
+
+
+def mspatial_stations(case: Case, omin, omax, oinc, bmin, bmax, binc, ind1: int, ind2: int, ind_inc: int, workdir: str = ".",
+                      outdir: Optional[str] = None, want_vectors: Optional[bool] = None):
+    """The full mspatial driver (mspatial.f90:20-96): for the stations ind1..ind2 (1-based rows of `delta.dat`), x = xb(ind),
+    Yi = 2 delta(ind), mean flow from `profile.<ind>`; at every station the (omega, beta) grid in the reference's loop
+    order; `iver` keeps counting across stations.  One batched GPU call per station (the grid and the mean flow change
+    with the station)."""
+    xb, delta = read_delta(os.path.join(workdir, "delta.dat"))
+    if ind1 < 1 or ind2 > xb.size:
+        raise B.StabGpuError("ERROR: illegal index...check delta.dat")          # mspatial.f90:46-50
+    if ind_inc == 0:
+        ind_inc = 1
+    out, iver = [], 0
+    for ind in range(ind1, ind2 + 1, ind_inc):
+        st = dataclasses.replace(case, params=case.params.copy(), itype=2, ind=ind, x=float(xb[ind - 1]))
+        st.params.yi = 2.0 * float(delta[ind - 1])
+        st.params.x = st.x
+        st.load_profile(os.path.join(workdir, f"profile.{ind}"))
+        r = mspatial(st, omin, omax, oinc, bmin, bmax, binc, outdir=None, want_vectors=want_vectors)
+        if outdir is not None:
+            for k in range(r["omega"].size):
+                _write(st, os.path.join(outdir, makename("eig", iver + k + 1)), 2, complex(r["omega"][k]), st.alpha,
+                       complex(r["beta"][k]), r["alp"][k], None if r["evec"] is None else r["evec"][k])
+        r.update(ind=ind, x=st.x, yi=st.params.yi, iver0=iver + 1)
+        iver += r["omega"].size
+        out.append(r)
+    return out
+

@@ -548,6 +548,31 @@ def test_cli_harness_writes_reference_records(tmp_path):
     assert abs(b3["alpha"] - 0.3) < 1e-15 and "evec" not in b3
 
 
+def test_mspatial_stations_delta_dat(tmp_path):
+    """mspatial.f90:20-96: station loop over delta.dat (x = xb(ind), Yi = 2 delta(ind), profile.<ind>), the (omega, beta) grid
+    at every station, `iver` counting across stations; each station equals a direct spatial call on its own grid."""
+    prof = golden_text("ts_profile.0")
+    for ind in (1, 2, 3):
+        (tmp_path / f"profile.{ind}").write_text(prof)
+    (tmp_path / "delta.dat").write_text("# x_body  delta\n 10.0 0.5\n# comment in the middle\n 20.0 0.45\n 30.0 0.6\n")
+    case = sb.read_deck(golden_text("ts_spatial_ny32.inp"))
+    out = sb.mspatial_stations(case, 0.06, 0.08, 0.02, 0.0, 0.0, 0.0, 2, 3, 1, workdir=str(tmp_path), outdir=str(tmp_path), want_vectors=False)
+    assert [r["ind"] for r in out] == [2, 3] and [r["iver0"] for r in out] == [1, 3]
+    assert [r["yi"] for r in out] == [0.9, 1.2] and [r["x"] for r in out] == [20.0, 30.0]
+    assert sorted(f for f in os.listdir(tmp_path) if f.startswith("eig.")) == ["eig.1", "eig.2", "eig.3", "eig.4"]
+    for r in out:
+        assert np.all(r["info"] == 0) and r["omega"].tolist() == [0.06, 0.08]          # upper end included (mspatial.f90:72, q6)
+        p, g = oracle_case("ts_spatial_ny32.inp", "ts_profile.0", yi=r["yi"], x=r["x"])
+        p.omega = 0.08 + 0j
+        ref = so.solve_spatial(p, g["vm"], g["deta"], g["d2eta"], g["hm"], want_vectors=False)["alp"]
+        fin = (np.abs(ref) > 1e-8) & (np.abs(ref) < 2.0)
+        _, d = match_spectra(ref[fin], r["alp"][1])
+        assert np.median(d / np.abs(ref[fin])) < 1e-10
+    recs = so.read_eig_file((tmp_path / "eig.4").read_bytes())
+    assert abs(recs["omega"] - 0.08) < 1e-15 and recs["ind"] == 3 and recs["x"] == 30.0 and recs["yi"] == 1.2
+    assert np.array_equal(recs["eval"], out[1]["alp"][1])
+
+
 def test_ider0_analytic_derivatives_getmean2(tmp_path):
     """ider=0 (getmean2.f90:26-187, temporal.f90:99-103): the mean derivatives come from first.<ind> /
     second.<ind> tables instead of D1/D2.  Tables here are finite differences of the shipped profile."""
