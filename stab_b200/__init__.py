@@ -39,7 +39,7 @@ from .binding import (  # noqa: F401
     debug_stages,
     debug_spatial_reduce,
 )
-from .api import Case, read_deck, spatial, temporal, mtemporal, mspatial, mspatial_stations, read_delta  # noqa: F401
+from .api import Case, read_deck, spatial, temporal, mtemporal, mspatial, mspatial_stations, read_delta, stab  # noqa: F401
 from . import post  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

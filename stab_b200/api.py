@@ -210,3 +210,33 @@ def mspatial_stations(case: Case, omin, omax, oinc, bmin, bmax, binc, ind1: int,
         out.append(r)
     return out
 
+
+def stab(deck_text: str, workdir: str = ".", name: str = "evec.dat"):
+    """The main program's dispatch (stab.f90:40-92) for the Chebyshev path: itype 1 temporal, 2 spatial, 7 mtemporal,
+    8 mspatial; mean flow from `profile.<ind>` (and `first.<ind>`, `second.<ind>` when ider=0) in `workdir`, results
+    written there as `evec.dat` / `eig.<iver>`.  The finite-difference, Stokes and bump solvers (itype 3-6, 9) are outside
+    the supported path."""
+    case = read_deck(deck_text)
+
+    def load(c: Case):
+        f = [os.path.join(workdir, f"{b}.{c.ind}") for b in ("profile", "first", "second")]
+        return c.load_profile(f[0], f[1], f[2]) if c.params.ider == 0 else c.load_profile(f[0])
+
+    if case.itype == 1:
+        return temporal(load(case), os.path.join(workdir, name))
+    if case.itype == 2:
+        return spatial(load(case), os.path.join(workdir, name))
+    rows = [[float(v) for v in _tokens(ln)] for ln in case.tail if _tokens(ln)]
+    if case.itype == 7:                                   # mtemporal(ind): `ind` is never read for this itype (stays 0)
+        case.itype = 1
+        (amin, amax, ainc), (bmin, bmax, binc) = rows[0][:3], rows[1][:3]
+        return mtemporal(load(case), amin, amax, ainc, bmin, bmax, binc, outdir=workdir, want_vectors=case.params.ievec == 1)
+    if case.itype == 8:
+        case.itype = 2
+        (omin, omax, oinc), (bmin, bmax, binc) = rows[0][:3], rows[1][:3]
+        ind1, ind2, ind_inc = (int(v) for v in rows[2][:3])
+        if len(rows) > 3 and int(rows[3][0]) != 0:
+            raise B.StabGpuError("mspatial: dtype=1 (finite differences) is outside the supported path")
+        return mspatial_stations(case, omin, omax, oinc, bmin, bmax, binc, ind1, ind2, ind_inc, workdir=workdir, outdir=workdir)
+    raise B.StabGpuError(f"itype = {case.itype} is outside the supported path (1, 2, 7, 8)")
+

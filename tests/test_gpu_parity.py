@@ -573,6 +573,31 @@ def test_mspatial_stations_delta_dat(tmp_path):
     assert np.array_equal(recs["eval"], out[1]["alp"][1])
 
 
+def test_stab_main_dispatch(tmp_path):
+    """stab.f90:40-92 through the host mirror: itype 1 writes evec.dat, itype 7 one eig.<iver> per (alpha, beta) point,
+    itype 8 runs the station loop, anything else is refused."""
+    (tmp_path / "profile.0").write_text(golden_text("ts_profile.0"))
+    (tmp_path / "profile.1").write_text(golden_text("ts_profile.0"))
+    (tmp_path / "delta.dat").write_text(" 0.0 0.5\n")
+    deck = golden_text("ts_temporal_ny96.inp").splitlines()         # positional deck: line 3 = Ny Yi Ymax, line 7 = itype
+    small = deck[:2] + ["24 1.0 0.0"] + deck[3:]
+    r = sb.stab("\n".join(small), workdir=str(tmp_path))
+    rec = so.read_eig_file((tmp_path / "evec.dat").read_bytes())
+    assert r["info"] == 0 and rec["itype"] == 1 and rec["ny"] == 24 and np.array_equal(rec["eval"], r["omg"])
+    sweep = small[:6] + ["7", "0.25 0.35 0.05", "0.0 0.1 1.0"]
+    out = sb.stab("\n".join(sweep), workdir=str(tmp_path))
+    assert np.allclose(out["alpha"], [0.25, 0.30]) and np.all(out["info"] == 0)
+    assert abs(so.read_eig_file((tmp_path / "eig.2").read_bytes())["alpha"] - 0.30) < 1e-15
+    sp = golden_text("ts_spatial_ny32.inp").splitlines()
+    ms = sp[:6] + ["8", "0.08 0.08 0.0", "0.0 0.0 0.0", "1 1 1", "0"]
+    st = sb.stab("\n".join(ms), workdir=str(tmp_path))
+    assert len(st) == 1 and st[0]["yi"] == 1.0 and np.all(st[0]["info"] == 0)
+    target = complex(2.2805022654496E-001, -6.5136925762007E-003)              # test/space.1:3: Yi = 2 * 0.5 = 1 is the deck's own grid
+    assert np.abs(st[0]["alp"][0] - target).min() < 1e-10
+    with pytest.raises(sb.StabGpuError):
+        sb.stab("\n".join(small[:6] + ["5", "0"]), workdir=str(tmp_path))
+
+
 def test_ider0_analytic_derivatives_getmean2(tmp_path):
     """ider=0 (getmean2.f90:26-187, temporal.f90:99-103): the mean derivatives come from first.<ind> /
     second.<ind> tables instead of D1/D2.  Tables here are finite differences of the shipped profile."""
