@@ -377,6 +377,7 @@ def main():
         while k < ihi:
             for c in range(k, min(k + NB, ihi)):
                 gemv_bytes += 16.0 * (ihi - k) * (ihi - c)           # y = A(k+1:ihi, c+1:ihi) v, one pass over the block
+                gemv_bytes += 16.0 * (c - k) * (ihi - c)             # + t = V(:,0:j)^H v_j in the same launch (one pass over V(c+1:ihi, 0:j))
             nct = n - (k + NB)
             gemm_flops += 8.0 * NB * ((k + 1) * (ihi - k) + (k + 1) * (NB - 1))
             if nct > 0:
@@ -398,7 +399,7 @@ def main():
     gemv_ms, gemm_ms = hess_bd.get("gemv", 0.0), hess_bd.get("gemm", 0.0)
     gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
     gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline_gemv = {"kernel": "k_hb_gemv (dominant kernel of the Hessenberg stage)", "bound": "hbm", "achieved": gemv_gbs,
+    roofline_gemv = {"kernel": "k_hb_gemv (dominant kernel of the Hessenberg stage: the GEMV of column j and, in one extra CTA per matrix, the V^H v_j dot products)", "bound": "hbm", "achieved": gemv_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": gemv_gbs / hbm_peak if hbm_peak else None,
                      "algorithmic_bytes_per_step": gemv_bytes, "ms_per_step": gemv_ms, "launches_per_step": 32 * int(np.ceil((n - 1) / 32)),
                      "peak_source": hbm_src,

@@ -35,6 +35,7 @@ struct HessBatch {
   int P;
   int mat0;             // first matrix of this launch group (the batch is split over two streams)
   cplx* Vx;             // n x NB per matrix: the current panel's V with explicit ones / zeros (pipelined GEMM path)
+  cplx* tv = nullptr;   // NB per matrix: t = V(:,0:j)^H v_j of the column whose GEMV is running (cta_hb_vdots)
   cplx* S = nullptr;    // NB x NB per matrix: V^H Y of the current panel (fused trailing update)
   cplx* Vh = nullptr;   // NB x n per matrix: conj(V(k+NB+j, :)) as a plain NB x nc operand (fused trailing update)
 };
@@ -76,25 +77,9 @@ SD_DEV void cta_hb_panel_step(const Cta& c, const HessBatch& hb, int mat, int pa
     const int jp = j - 1, cp = k + jp;
     const bool fin = cp < ihi;
     const cplx taup = fin ? tau[cp] : mk(0.0, 0.0);
-    if (fin) {
-      const cplx* vcol = A + (size_t)cp * lda;
-      for (int l = c.wid; l < jp; l += c.nw) {             // t = V(:,0:jp)^H v_jp
-        const cplx* vl = A + (size_t)(k + l) * lda;
-        cplx s = mk(0.0, 0.0);
-        for (int r0 = cp + 1 + c.lane; r0 <= ihi; r0 += HB_DU * c.ws) {   // HB_DU loads in flight per operand
-          cplx a[HB_DU], b[HB_DU];
-#pragma unroll
-          for (int u = 0; u < HB_DU; ++u) {
-            const int r = r0 + u * c.ws;
-            a[u] = (r <= ihi) ? vl[r] : mk(0.0, 0.0);
-            b[u] = (r <= ihi) ? ((r == cp + 1) ? mk(1.0, 0.0) : vcol[r]) : mk(0.0, 0.0);
-          }
-#pragma unroll
-          for (int u = 0; u < HB_DU; ++u) fma_acc_conj(s, a[u], b[u]);
-        }
-        s = warp_sum(s);
-        if (c.lane == 0) st[l] = s;
-      }
+    if (fin) {                                             // t = V(:,0:jp)^H v_jp: computed beside the GEMV (cta_hb_vdots)
+      const cplx* tv = hb.tv + (size_t)mat * HB_NB;
+      for (int l = c.tid; l < jp; l += c.nt) st[l] = tv[l];
     }
     if (have_col)
       for (int l = c.tid; l < j; l += c.nt) sc[l] = conj(hb_v(A, lda, k, ihi, col, l));
@@ -207,6 +192,36 @@ SD_DEV void cta_hb_gemv(const Cta& c, const HessBatch& hb, int mat, int panel, i
     }
     for (; cc < c1; ++cc) fma_acc(a0, ap[(size_t)cc * lda], sv[cc - c0]);
     Yp[r] = (a0 + a1) + (a2 + a3);
+  }
+}
+
+// t = V(:,0:j)^H v_j for the column whose GEMV is in flight (ZLAHR2's  T(0:j,j) = -tau T V^H v  and  Y(:,j) -= Y t  need
+// it only AFTER the GEMV): one extra CTA per matrix in the GEMV launch, so that this pass over V runs in the shadow of the
+// bandwidth-bound GEMV instead of in the latency-bound panel step.  One warp per column l, HB_DU loads in flight per lane.
+SD_DEV void cta_hb_vdots(const Cta& c, const HessBatch& hb, int mat, int panel, int j) {
+  const int n = hb.n, lda = n;
+  const cplx* A = hb.A + (size_t)mat * hb.astride;
+  const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
+  const int k = ilo + panel * HB_NB, cp = k + j;
+  if (k >= ihi || cp >= ihi) return;
+  cplx* tv = hb.tv + (size_t)mat * HB_NB;
+  const cplx* vcol = A + (size_t)cp * lda;
+  for (int l = c.wid; l < j; l += c.nw) {
+    const cplx* vl = A + (size_t)(k + l) * lda;
+    cplx s = mk(0.0, 0.0);
+    for (int r0 = cp + 1 + c.lane; r0 <= ihi; r0 += HB_DU * c.ws) {
+      cplx a[HB_DU], b[HB_DU];
+#pragma unroll
+      for (int u = 0; u < HB_DU; ++u) {
+        const int r = r0 + u * c.ws;
+        a[u] = (r <= ihi) ? vl[r] : mk(0.0, 0.0);
+        b[u] = (r <= ihi) ? ((r == cp + 1) ? mk(1.0, 0.0) : vcol[r]) : mk(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < HB_DU; ++u) fma_acc_conj(s, a[u], b[u]);
+    }
+    s = warp_sum(s);
+    if (c.lane == 0) tv[l] = s;
   }
 }
 

@@ -236,6 +236,10 @@ __global__ void __launch_bounds__(512) k_hb_panel_step(HessBatch hb, int panel, 
 __global__ void __launch_bounds__(HB_GEMV_ROWS) k_hb_gemv(HessBatch hb, int panel, int j) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta c = make_cta(nullptr);
+  if (blockIdx.y == HB_CHUNKS) {                           // the extra chunk index: one CTA per matrix takes the V^H v dot products
+    if (blockIdx.x == 0) cta_hb_vdots(c, hb, hb.mat0 + blockIdx.z, panel, j);
+    return;
+  }
   cta_hb_gemv(c, hb, hb.mat0 + blockIdx.z, panel, j, blockIdx.x, blockIdx.y, reinterpret_cast<cplx*>(smem_raw));
 }
 

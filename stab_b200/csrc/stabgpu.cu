@@ -106,7 +106,7 @@ struct stabgpu_plan {
   bool has_Re = false, has_Ma = false;
   // work
   DBuf<cplx> coef, A, C, Hq, V, tau, w, eig, lam;
-  DBuf<cplx> hbY, hbT, hbYp, hbW, hbVx, hbS, hbVh;   // blocked Hessenberg workspaces (Vx: the panel's V with explicit ones / zeros)
+  DBuf<cplx> hbY, hbT, hbYp, hbW, hbVx, hbS, hbVh, hbTv;   // blocked Hessenberg workspaces (Vx: the panel's V with explicit ones / zeros)
   int hbP = 0;
   DBuf<double> scale, hnorm;
   DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr, vbad, lu_perm;
@@ -158,7 +158,7 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
   pl->hbP = (N - 1 + HB_NB - 1) / HB_NB;
   if (pl->hbY.alloc((size_t)cap * N * HB_NB) || pl->hbT.alloc((size_t)cap * pl->hbP * HB_NB * HB_NB) ||
       pl->hbYp.alloc((size_t)cap * N * HB_CHUNKS) || pl->hbW.alloc((size_t)cap * N * HB_NB) || pl->hbVx.alloc((size_t)cap * N * HB_NB) ||
-      pl->hbS.alloc((size_t)cap * HB_NB * HB_NB) || pl->hbVh.alloc((size_t)cap * N * HB_NB)) return 1;
+      pl->hbS.alloc((size_t)cap * HB_NB * HB_NB) || pl->hbVh.alloc((size_t)cap * N * HB_NB) || pl->hbTv.alloc((size_t)cap * HB_NB)) return 1;
   if (pl->ilohi.alloc(2 * (size_t)cap) || pl->info_lu.alloc(cap) || pl->info_qr.alloc(cap) || pl->info_v.alloc(cap)) return 1;
   CU(cudaStreamCreate(&pl->stream));
   CU(cudaStreamCreate(&pl->stream2));
@@ -231,7 +231,7 @@ int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, 
   if (rows_max <= 0) return 0;
   const int trail_max = N - (k0 + HB_NB);                    // columns k+NB..n-1
   if (phase == 1) {
-    dim3 ggemv((rows_max + HB_GEMV_ROWS - 1) / HB_GEMV_ROWS, HB_CHUNKS, nmat);
+    dim3 ggemv((rows_max + HB_GEMV_ROWS - 1) / HB_GEMV_ROWS, HB_CHUNKS + 1, nmat);   // + the V^H v dot products of the same column
     for (int j = 0; j < HB_NB; ++j) {
       k_hb_panel_step<<<nmat, pst, sm_step, s>>>(hb, p, j);
       if (hmark(pl, s, 0)) return 1;
@@ -316,7 +316,7 @@ int run_hessenberg(stabgpu_plan* pl) {
     return 0;
   }
   const bool mma = g_tune.hess_mode == 1 || g_tune.hess_mode == 3;   // 1: pipelined DMMA kernels, 3: the tile-per-CTA DMMA kernels
-  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p, pl->hbS.p, pl->hbVh.p};
+  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p, pl->hbTv.p, pl->hbS.p, pl->hbVh.p};
   pl->pev_n = 0;
   if (hmark(pl, s, 3)) return 1;
   const int half = (g_tune.hess_streams >= 2 && np >= 16) ? (np + 1) / 2 : np;

@@ -190,12 +190,15 @@ extern "C" int emu_hess_blocked(cplx* A, int n, int ilo, int ihi, cplx* tau, cpl
   std::vector<double> smem(GemmCfg<64, 64>::smem_bytes / sizeof(double));
   int ilohi[2] = {ilo, ihi};
   HessBatch hb{A, (size_t)n * n, n, ilohi, tau, Y.data(), T.data(), Yp.data(), W.data(), P, 0};
+  std::vector<cplx> tv(HB_NB);
+  hb.tv = tv.data();
   const int tiles = (n + 63) / 64;
   for (int p = 0; p < P; ++p) {
     for (int j = 0; j < HB_NB; ++j) {
       cta_hb_panel_step(c, hb, 0, p, j, red.data(), sb.data(), sw.data(), st.data(), scv.data());
       for (int rt = 0; rt * HB_GEMV_ROWS < n; ++rt)
         for (int ch = 0; ch < HB_CHUNKS; ++ch) cta_hb_gemv(c, hb, 0, p, j, rt, ch, sv.data());
+      cta_hb_vdots(c, hb, 0, p, j);                       // runs beside the GEMV on the device
     }
     cta_hb_panel_step(c, hb, 0, p, HB_NB, red.data(), sb.data(), sw.data(), st.data(), scv.data());
     for (int ti = 0; ti < tiles; ++ti) cta_hb_gemm<HB_YTOP, false>(c, hb, 0, p, ti, 0, smem.data());
