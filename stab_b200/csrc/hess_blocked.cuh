@@ -35,6 +35,8 @@ struct HessBatch {
   int P;
   int mat0;             // first matrix of this launch group (the batch is split over two streams)
   cplx* Vx;             // n x NB per matrix: the current panel's V with explicit ones / zeros (pipelined GEMM path)
+  cplx* VT = nullptr;   // n x NB per matrix: Vx T   (pipelined path: folds the triangular factor into the GEMM operand,
+  cplx* VTh = nullptr;  // n x NB per matrix: Vx T^H  so that no separate pass applies T to Y_top / W)
   cplx* tv = nullptr;   // NB per matrix: t = V(:,0:j)^H v_j of the column whose GEMV is running (cta_hb_vdots)
   cplx* S = nullptr;    // NB x NB per matrix: V^H Y of the current panel (fused trailing update)
   cplx* Vh = nullptr;   // NB x n per matrix: conj(V(k+NB+j, :)) as a plain NB x nc operand (fused trailing update)

@@ -252,18 +252,54 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_hb_gemm(HessBatch hb, int p
 
 #ifndef STAB_EMU
 // ---- pipelined DMMA GEMM path (gemm_pipe.cuh): plain operands, V materialised per panel ----------
-// Vx(r, l) = V(r, l) of the panel (zeros above / beyond the reflector, explicit one); grid (row blocks, batch)
-__global__ void k_hb_vx(HessBatch hb, int panel) {
+// Vx(r, l) = V(r, l) of the panel (zeros above / beyond the reflector, explicit one); grid (row blocks, batch).
+// want bit 0: also VT = Vx T (the operand of Y_top = A_top (V T) and of the back-transformation X -= (V T)(V^H X));
+// want bit 1: also VTh = Vx T^H (the operand of the left update A -= (V T^H)(V^H A)).  T is upper triangular, so a row
+// costs 528 complex FMAs per product, from registers, with coalesced loads and stores -- this replaces the passes that
+// applied T to Y_top and to W (one thread per column with stride-32 accesses: 9.8 ms per 296 points at n = 640).
+__global__ void __launch_bounds__(128) k_hb_vx(HessBatch hb, int panel, int want) {
+  __shared__ cplx sT[HB_NB * HB_NB];
   const int mat = hb.mat0 + blockIdx.y, n = hb.n;
   const int ilo = hb.ilohi[2 * mat], ihi = hb.ilohi[2 * mat + 1];
   const int k = ilo + panel * HB_NB;
   if (k >= ihi) return;
+  if (want) {
+    const cplx* T = hb.T + ((size_t)mat * hb.P + panel) * HB_NB * HB_NB;
+    for (int e = threadIdx.x; e < HB_NB * HB_NB; e += blockDim.x) sT[e] = T[e];
+    __syncthreads();
+  }
   const cplx* A = hb.A + (size_t)mat * hb.astride;
   cplx* Vx = hb.Vx + (size_t)mat * n * HB_NB;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-#pragma unroll 8
-  for (int l = 0; l < HB_NB; ++l) Vx[r + (size_t)l * n] = hb_v(A, n, k, ihi, r, l);
+  cplx v[HB_NB];
+#pragma unroll
+  for (int l = 0; l < HB_NB; ++l) { v[l] = hb_v(A, n, k, ihi, r, l); Vx[r + (size_t)l * n] = v[l]; }
+  const bool zero = (r <= k) || (r > ihi);
+  if (want & 1) {
+    cplx* VT = hb.VT + (size_t)mat * n * HB_NB;
+#pragma unroll
+    for (int m = 0; m < HB_NB; ++m) {
+      cplx s = mk(0.0, 0.0);
+      if (!zero) {
+#pragma unroll
+        for (int l = 0; l <= m; ++l) fma_acc(s, v[l], sT[l + m * HB_NB]);
+      }
+      VT[r + (size_t)m * n] = s;
+    }
+  }
+  if (want & 2) {
+    cplx* VTh = hb.VTh + (size_t)mat * n * HB_NB;
+#pragma unroll
+    for (int m = 0; m < HB_NB; ++m) {
+      cplx s = mk(0.0, 0.0);
+      if (!zero) {
+#pragma unroll
+        for (int l = m; l < HB_NB; ++l) fma_acc_conj(s, sT[m + l * HB_NB], v[l]);       // conj(T(m,l)) v(l)
+      }
+      VTh[r + (size_t)m * n] = s;
+    }
+  }
 }
 
 enum PipePhase { PP_YTOP = 0, PP_RIGHT_TRAIL, PP_RIGHT_PANEL, PP_LEFT_W, PP_LEFT_UPD, PP_BT_W, PP_BT_UPD, PP_RIGHT_TOP, PP_S, PP_FUSED_UPD };
@@ -282,10 +318,12 @@ struct HbProb {
     cplx* Y = hb.Y + (size_t)mat * n * HB_NB;
     cplx* W = hb.W + (size_t)mat * n * HB_NB;
     const cplx* Vx = hb.Vx + (size_t)mat * n * HB_NB;
+    const cplx* VT = hb.VT ? hb.VT + (size_t)mat * n * HB_NB : Vx;       // T folded into the operand (then no pass applies T afterwards)
+    const cplx* VTh = hb.VTh ? hb.VTh + (size_t)mat * n * HB_NB : Vx;
     if (PHASE == PP_YTOP) {                 // Y(0:k+1, :) = A(0:k+1, k+1:ihi+1) V(k+1:ihi+1, :)
       q.m = k + 1; q.nc = HB_NB; q.K = ihi - k;
       q.L = A + (size_t)(k + 1) * lda; q.lsi = 1; q.lsl = lda;
-      q.R = Vx + (k + 1); q.rsl = 1; q.rsj = n;
+      q.R = VT + (k + 1); q.rsl = 1; q.rsj = n;
       q.C = Y; q.ldc = n;
     } else if (PHASE == PP_RIGHT_TRAIL) {   // A(0:ihi+1, k+NB:ihi+1) -= Y V(k+NB:ihi+1, :)^H
       q.m = ihi + 1; q.nc = ihi + 1 - (k + HB_NB); q.K = HB_NB;
@@ -304,7 +342,7 @@ struct HbProb {
       q.C = W; q.ldc = HB_NB;
     } else if (PHASE == PP_LEFT_UPD) {      // A(k+1:ihi+1, k+NB:n) -= V W
       q.m = ihi - k; q.nc = n - (k + HB_NB); q.K = HB_NB;
-      q.L = Vx + (k + 1); q.lsi = 1; q.lsl = n;
+      q.L = VTh + (k + 1); q.lsi = 1; q.lsl = n;
       q.R = W; q.rsl = 1; q.rsj = HB_NB;
       q.C = A + (k + 1) + (size_t)(k + HB_NB) * lda; q.ldc = lda;
     } else if (PHASE == PP_RIGHT_TOP) {     // A(0:k+1, k+NB:ihi+1) -= Y(0:k+1, :) V(k+NB:ihi+1, :)^H   (rows above the panel only)
@@ -332,7 +370,7 @@ struct HbProb {
     } else {                                // X(k+1:ihi+1, :) -= V W
       cplx* Xm = X + (size_t)mat * xstride;
       q.m = ihi - k; q.nc = n; q.K = HB_NB;
-      q.L = Vx + (k + 1); q.lsi = 1; q.lsl = n;
+      q.L = VT + (k + 1); q.lsi = 1; q.lsl = n;
       q.R = W; q.rsl = 1; q.rsj = HB_NB;
       q.C = Xm + (k + 1); q.ldc = n;
     }

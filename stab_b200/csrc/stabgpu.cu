@@ -106,7 +106,7 @@ struct stabgpu_plan {
   bool has_Re = false, has_Ma = false;
   // work
   DBuf<cplx> coef, A, C, Hq, V, tau, w, eig, lam;
-  DBuf<cplx> hbY, hbT, hbYp, hbW, hbVx, hbS, hbVh, hbTv;   // blocked Hessenberg workspaces (Vx: the panel's V with explicit ones / zeros)
+  DBuf<cplx> hbY, hbT, hbYp, hbW, hbVx, hbS, hbVh, hbTv, hbVT, hbVTh;   // blocked Hessenberg workspaces (Vx: the panel's V with explicit ones / zeros)
   int hbP = 0;
   DBuf<double> scale, hnorm;
   DBuf<int> cnt, ilohi, info_lu, info_qr, info_v, blkend, kr, vbad, lu_perm;
@@ -131,7 +131,7 @@ size_t per_point_bytes(int kind, int n, int N, int ny, int want_vectors) {
   if (want_vectors) b += 2 * (size_t)N * N * 16;     // Hq + V
   b += (size_t)ny * 150 * 16;                        // coefficients
   b += (size_t)N * (16 * 4 + 8 + 4 * 3) + 64;
-  b += (size_t)N * 16 * (5 * HB_NB + HB_CHUNKS) + 2 * 16 * HB_NB * HB_NB;   // blocked Hessenberg: Y, W, Vx, Vh, T, S, Ypart
+  b += (size_t)N * 16 * (7 * HB_NB + HB_CHUNKS) + 3 * 16 * HB_NB * HB_NB;   // blocked Hessenberg: Y, W, Vx, Vh, T, S, Ypart
   return b;
 }
 
@@ -158,7 +158,8 @@ int plan_alloc(stabgpu_plan* pl, int max_pts) {
   pl->hbP = (N - 1 + HB_NB - 1) / HB_NB;
   if (pl->hbY.alloc((size_t)cap * N * HB_NB) || pl->hbT.alloc((size_t)cap * pl->hbP * HB_NB * HB_NB) ||
       pl->hbYp.alloc((size_t)cap * N * HB_CHUNKS) || pl->hbW.alloc((size_t)cap * N * HB_NB) || pl->hbVx.alloc((size_t)cap * N * HB_NB) ||
-      pl->hbS.alloc((size_t)cap * HB_NB * HB_NB) || pl->hbVh.alloc((size_t)cap * N * HB_NB) || pl->hbTv.alloc((size_t)cap * HB_NB)) return 1;
+      pl->hbS.alloc((size_t)cap * HB_NB * HB_NB) || pl->hbVh.alloc((size_t)cap * N * HB_NB) || pl->hbTv.alloc((size_t)cap * HB_NB) ||
+      pl->hbVT.alloc((size_t)cap * N * HB_NB) || pl->hbVTh.alloc((size_t)cap * N * HB_NB)) return 1;
   if (pl->ilohi.alloc(2 * (size_t)cap) || pl->info_lu.alloc(cap) || pl->info_qr.alloc(cap) || pl->info_v.alloc(cap)) return 1;
   CU(cudaStreamCreate(&pl->stream));
   CU(cudaStreamCreate(&pl->stream2));
@@ -202,8 +203,8 @@ int launch_pipe(stabgpu_plan* pl, const HessBatch& hb, cplx* X, size_t xstride, 
   pl->launches += 1;
   return 0;
 }
-int launch_vx(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, int panel) {
-  k_hb_vx<<<dim3((hb.n + 127) / 128, nmat), 128, 0, s>>>(hb, panel);
+int launch_vx(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, int panel, int want = 0) {
+  k_hb_vx<<<dim3((hb.n + 127) / 128, nmat), 128, 0, s>>>(hb, panel, want);
   CU(cudaGetLastError());
   pl->launches += 1;
   return 0;
@@ -263,18 +264,14 @@ int hess_panel(stabgpu_plan* pl, const HessBatch& hb, int nmat, cudaStream_t s, 
     CU(cudaGetLastError());
     return 0;
   }
-  if (g_tune.hess_mode == 1) {               // pipelined path: plain operands (V materialised), persistent cp.async ring
-    if (launch_vx(pl, hb, nmat, s, p)) return 1;
-    if (launch_pipe<PP_YTOP>(pl, hb, nullptr, 0, nmat, s, p, tm, 1)) return 1;
-    k_hb_ytop_T<<<dim3((N + 127) / 128, nmat), 128, 0, s>>>(hb, p);
-    pl->launches += 1;
+  if (g_tune.hess_mode == 1) {               // pipelined path: plain operands (V, V T, V T^H materialised), persistent cp.async ring
+    if (launch_vx(pl, hb, nmat, s, p, 3)) return 1;
+    if (launch_pipe<PP_YTOP>(pl, hb, nullptr, 0, nmat, s, p, tm, 1)) return 1;                 // Y_top = A_top (V T)
     if (trail_max > 0 && launch_pipe<PP_RIGHT_TRAIL>(pl, hb, nullptr, 0, nmat, s, p, tm, (trail_max + 31) / 32)) return 1;
     if (launch_pipe<PP_RIGHT_PANEL>(pl, hb, nullptr, 0, nmat, s, p, tm, 1)) return 1;
     if (trail_max > 0) {
-      if (launch_pipe<PP_LEFT_W>(pl, hb, nullptr, 0, nmat, s, p, 1, (trail_max + 63) / 64)) return 1;
-      k_hb_w_T<<<dim3((trail_max + 127) / 128, nmat), 128, 0, s>>>(hb, p);
-      pl->launches += 1;
-      if (launch_pipe<PP_LEFT_UPD>(pl, hb, nullptr, 0, nmat, s, p, (rows_max + 63) / 64, (trail_max + 31) / 32)) return 1;
+      if (launch_pipe<PP_LEFT_W>(pl, hb, nullptr, 0, nmat, s, p, 1, (trail_max + 63) / 64)) return 1;   // W = V^H A
+      if (launch_pipe<PP_LEFT_UPD>(pl, hb, nullptr, 0, nmat, s, p, (rows_max + 63) / 64, (trail_max + 31) / 32)) return 1;   // A -= (V T^H) W
     }
     if (hmark(pl, s, 2)) return 1;
     CU(cudaGetLastError());
@@ -316,7 +313,8 @@ int run_hessenberg(stabgpu_plan* pl) {
     return 0;
   }
   const bool mma = g_tune.hess_mode == 1 || g_tune.hess_mode == 3;   // 1: pipelined DMMA kernels, 3: the tile-per-CTA DMMA kernels
-  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p, pl->hbTv.p, pl->hbS.p, pl->hbVh.p};
+  HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, 0, pl->hbVx.p,
+               g_tune.hess_mode == 1 ? pl->hbVT.p : nullptr, g_tune.hess_mode == 1 ? pl->hbVTh.p : nullptr, pl->hbTv.p, pl->hbS.p, pl->hbVh.p};
   pl->pev_n = 0;
   if (hmark(pl, s, 3)) return 1;
   const int half = (g_tune.hess_streams >= 2 && np >= 16) ? (np + 1) / 2 : np;
@@ -432,17 +430,16 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
       CU(cudaGetLastError());
       pl->launches += 1;
       if (hmark(pl, s, 4)) return 1;
-      HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, m0, pl->hbVx.p};
+      HessBatch hb{pl->A.p, st, N, pl->ilohi.p, pl->tau.p, pl->hbY.p, pl->hbT.p, pl->hbYp.p, pl->hbW.p, pl->hbP, m0, pl->hbVx.p,
+                   (g_tune.hess_mode == 1 || g_tune.hess_mode == 5) ? pl->hbVT.p : nullptr};
       const int tn = (N + 63) / 64;
       for (int p = pl->hbP - 1; p >= 0; --p) {
         const int rows_max = N - 1 - p * HB_NB;
         if (rows_max <= 0) continue;
         if (g_tune.hess_mode == 1 || g_tune.hess_mode == 5) {
-          if (launch_vx(pl, hb, cnt, s, p)) return 1;
-          if (launch_pipe<PP_BT_W>(pl, hb, pl->V.p, st, cnt, s, p, 1, tn)) return 1;
-          k_bt_w_T<<<dim3((N + 127) / 128, cnt), 128, 0, s>>>(hb, p);
-          pl->launches += 1;
-          if (launch_pipe<PP_BT_UPD>(pl, hb, pl->V.p, st, cnt, s, p, (rows_max + 63) / 64, (N + 31) / 32)) return 1;
+          if (launch_vx(pl, hb, cnt, s, p, 1)) return 1;                                                   // V and V T
+          if (launch_pipe<PP_BT_W>(pl, hb, pl->V.p, st, cnt, s, p, 1, tn)) return 1;                        // W = V^H X
+          if (launch_pipe<PP_BT_UPD>(pl, hb, pl->V.p, st, cnt, s, p, (rows_max + 63) / 64, (N + 31) / 32)) return 1;   // X -= (V T) W
           continue;
         }
         if (launch_bt_gemm<BT_W>(pl, hb, cnt, p, 1, tn, GemmCfg<32, 64>::smem_bytes)) return 1;
