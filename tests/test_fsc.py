@@ -86,3 +86,17 @@ def test_cf_spatial_thesis_space_ref():
     assert abs(r["alp"][j] - target) < 1e-8
     rows = so.getevec_rows(r["y"], r["evec"][:, j], p.ny)
     assert np.abs(rows - _rows("cf_thesis_spatial_ny96.space.ref")).max() < 1e-7
+
+
+def test_deck_errors_and_delta_reader(tmp_path):
+    import stab_b200 as sb
+    with pytest.raises(ValueError):
+        fsc.read_deck("0.3 400\n45\n")                       # truncated deck
+    with pytest.raises(ValueError):
+        fsc.profile_from_deck(golden_text("cf_thesis_fsc.inp").replace("1, 1, 1", "1, 0, 1"))   # cooled wall: not the supported case
+    (tmp_path / "delta.dat").write_text("# x  delta\n 1.0  0.25\n# mid comment\n 2.0, 0.5\n\n")
+    xb, d = sb.read_delta(str(tmp_path / "delta.dat"))
+    assert xb.tolist() == [1.0, 2.0] and d.tolist() == [0.25, 0.5]
+    fsc.write_profile(str(tmp_path), 3, fsc.solve(0.3, 0.0, 0.0, n=200, xi_max=10.0), derivatives=True)
+    tab = np.loadtxt(tmp_path / "profile.3")
+    assert tab.shape == (200, 6) and sorted(p.name for p in tmp_path.iterdir() if p.name.endswith(".3")) == ["first.3", "profile.3", "second.3"]
