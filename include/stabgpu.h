@@ -20,6 +20,8 @@
 #ifndef STABGPU_H
 #define STABGPU_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -44,7 +46,22 @@ typedef struct stabgpu_params {
 } stabgpu_params;
 
 /* ---- lifetime --------------------------------------------------------------------------------- */
-int stabgpu_init(int device);                 /* selects the CUDA device; <0: current device */
+int stabgpu_init(int device);                 /* ONE device: selects the CUDA device; <0: current device */
+/* The drop-in case: the reference is one serial process that walks the sweep point by point
+ * (mtemporal.f90:29-39, mspatial.f90:77-96).  After this call every stabgpu_*_batch / stabgpu_polish_batch call shards
+ * its points over the first min(max_devices, visible) GPUs of the box -- contiguous shards of stabgpu_shard_range, one
+ * host worker thread, one cached plan and one pinned staging ring per device -- and writes into the caller's single
+ * host arrays.  max_devices <= 0: all visible devices.  Results are bit-identical to the single-device call. */
+int stabgpu_init_multi(int max_devices, int* ndev_used);
+int stabgpu_device_count(void);               /* devices the batch calls shard over (0 before init) */
+/* Host staging of the eigenvector output.  A page-locked destination (cudaHostAlloc / stabgpu_host_register) receives
+ * the vectors by direct DMA under the eigenvector stage; a pageable one (a Fortran `allocate`, malloc, numpy) is served
+ * through a pinned staging ring inside the library (4 x 64 MB per device, DMA -> ring -> caller array by `copy_threads`
+ * host threads), so the overlap survives.  pin_mode 0 disables the ring (plain cudaMemcpyAsync into pageable memory);
+ * values < 0 / <= 0 keep the current setting. */
+int stabgpu_set_host_staging(int pin_mode, int copy_threads);
+int stabgpu_host_register(void* ptr, size_t bytes);    /* page-lock a caller array once (cudaHostRegister, portable) */
+int stabgpu_host_unregister(void* ptr);
 int stabgpu_finalize(void);
 const char* stabgpu_last_error(void);
 int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb);
@@ -102,10 +119,25 @@ int stabgpu_spatial_batch(const stabgpu_params* p, const double* vm, const doubl
  * A: n x n x batch (not modified); w: n x batch in ZGEEV-like (unsorted) order; V: n x n x batch or NULL. */
 int stabgpu_zgeev_batch(int n, int batch, const double* A, int want_vectors, double* w, double* V, int* info);
 
-/* Stage (4) of the north star: polish one mode of the temporal problem by shift-invert inverse
- * iteration on the pencil (A0 - sigma B0); new functionality (the reference's polishing tool
- * `shoot` is not in the repo).  x0 may be NULL.  Returns lambda, x (n, scaled as temporal.f90:867-879),
- * residual ||A0 x - lambda B0 x|| / (||A0 x|| + |lambda| ||B0 x||), iterations. */
+/* Stage (4) of the north star, batched: polish ONE mode per sweep point by shift-invert (residual) inverse iteration
+ * on the operator polynomial of that point, P(l) = A0 - l B0 (kind 1, temporal.f90:622-752; l = omega) or
+ * P(l) = C0 + l C1 + l^2 C2 (kind 2, spatial.f90:681-1016; l = alpha, x = the bottom half of the companion eigenvector).
+ * New functionality: the reference polishes with the external `shoot` (README.md:3-7, thesis/TStest/run.sh:30); getevec only
+ * selects a mode of the full spectrum (getevec.f90:154-222).  Per point: P(sigma_p) is factored once by the batched blocked LU
+ * (DMMA rank-32 updates), then every iteration is three n x n matrix-vector products and one replay of the factorization.
+ *   s1/s2: (alpha|omega, beta) per point as in the batch calls; sigma: the shift per point (e.g. the neighbouring point's
+ *   eigenvalue); x0: n x npts start vectors or NULL; h5: spatial curvature metrics or NULL.
+ *   lambda: polished eigenvalue per point; x: n x npts eigenvectors scaled as temporal.f90:867-879 (or NULL);
+ *   resid: |P(lambda) x| / (|M0 x| + |lambda||M1 x| + |lambda|^2 |M2 x|); iters: iterations used, or -(k+1) when the
+ *   k-th pivot of P(sigma) is exactly zero (sigma is an eigenvalue to working precision).  Shards over the devices of
+ *   stabgpu_init_multi like the batch calls. */
+int stabgpu_polish_batch(int kind, const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                         const double* deta, const double* d2eta, const double* h5,
+                         int npts, const double* s1, const double* s2, const double* Re_pt, const double* Ma_pt,
+                         const double* sigma /* 2*npts */, const double* x0 /* 2*n*npts or NULL */,
+                         int max_iters, double tol,
+                         double* lambda /* 2*npts */, double* x /* 2*n*npts or NULL */, double* resid, int* iters);
+/* one temporal point through the same path (kept for the round-1 callers) */
 int stabgpu_temporal_polish(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
                             const double* deta, const double* d2eta, const double* alpha, const double* beta,
                             const double* sigma, const double* x0, int max_iters, double tol,
@@ -151,7 +183,8 @@ int stabgpu_plan_capacity(stabgpu_plan* plan);                                  
 int stabgpu_plan_destroy(stabgpu_plan* plan);
 
 /* ---- sweep drivers and file formats (host) ------------------------------------------------------ */
-/* mtemporal.f90:25-39: point enumeration (upper end excluded, quirk q6). Returns npts. */
+/* mtemporal.f90:25-39: point enumeration (upper end excluded, quirk q6). Returns npts, or -1 for a zero / non-finite
+ * increment or more than 10^7 points (the reference divides by the increment unguarded). */
 int stabgpu_mtemporal_points(double amin, double amax, double ainc, double bmin, double bmax, double binc,
                              double* alpha_r, double* beta_r, int max_pts);
 /* mspatial.f90:68-96: upper end included. */

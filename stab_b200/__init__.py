@@ -18,6 +18,13 @@ from .binding import (  # noqa: F401
     edge_properties,
     getmean,
     init,
+    init_multi,
+    device_count,
+    set_host_staging,
+    host_register,
+    host_unregister,
+    finalize,
+    polish_batch,
     lib,
     mean_gradients,
     mspatial_points,

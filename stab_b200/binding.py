@@ -69,6 +69,11 @@ def lib():
 
     i, d, vp, cp = C.c_int, C.c_double, C.c_void_p, C.c_char_p
     proto("stabgpu_init", i, [i])
+    proto("stabgpu_init_multi", i, [i, _ip])
+    proto("stabgpu_device_count", i, [])
+    proto("stabgpu_set_host_staging", i, [i, i])
+    proto("stabgpu_host_register", i, [vp, C.c_size_t])
+    proto("stabgpu_host_unregister", i, [vp])
     proto("stabgpu_finalize", i, [])
     proto("stabgpu_last_error", cp, [])
     proto("stabgpu_device_info", i, [cp, i, _ip, _dp])
@@ -90,6 +95,7 @@ def lib():
     proto("stabgpu_spatial_batch", i, [_pp, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp])
     proto("stabgpu_zgeev_batch", i, [i, i, vp, i, vp, vp, vp])
     proto("stabgpu_temporal_polish", i, [_pp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, d, vp, vp, _dp, _ip])
+    proto("stabgpu_polish_batch", i, [i, _pp, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, d, vp, vp, vp, vp])
     proto("stabgpu_temporal_assemble", i, [_pp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
     proto("stabgpu_spatial_assemble", i, [_pp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
     proto("stabgpu_debug_stages", i, [i, vp, vp, vp, _ip, _ip, vp, vp])
@@ -200,6 +206,8 @@ def circh(radius: float, y: np.ndarray):
 
 def mtemporal_points(amin, amax, ainc, bmin, bmax, binc):
     n = lib().stabgpu_mtemporal_points(amin, amax, ainc, bmin, bmax, binc, None, None, 0)
+    if n < 0:
+        raise StabGpuError("mtemporal: zero / non-finite increment or more than 10^7 sweep points")
     a, b = np.empty(n), np.empty(n)
     lib().stabgpu_mtemporal_points(amin, amax, ainc, bmin, bmax, binc, _ptr(a), _ptr(b), n)
     return a, b
@@ -207,6 +215,8 @@ def mtemporal_points(amin, amax, ainc, bmin, bmax, binc):
 
 def mspatial_points(omin, omax, oinc, bmin, bmax, binc):
     n = lib().stabgpu_mspatial_points(omin, omax, oinc, bmin, bmax, binc, None, None, 0)
+    if n < 0:
+        raise StabGpuError("mspatial: non-finite range or more than 10^7 sweep points")
     a, b = np.empty(n), np.empty(n)
     lib().stabgpu_mspatial_points(omin, omax, oinc, bmin, bmax, binc, _ptr(a), _ptr(b), n)
     return a, b
@@ -232,6 +242,33 @@ def write_eig_file(path: str, p: Params, itype: int, ind: int, omega: complex, a
 # ---- device ---------------------------------------------------------------------------------------
 def init(device: int = -1):
     _check(lib().stabgpu_init(device), "stabgpu_init")
+
+
+def init_multi(max_devices: int = 0) -> int:
+    """stabgpu_init_multi: the batch calls shard over up to `max_devices` GPUs (0 = all).  Returns the device count."""
+    n = C.c_int(0)
+    _check(lib().stabgpu_init_multi(int(max_devices), C.byref(n)), "stabgpu_init_multi")
+    return n.value
+
+
+def device_count() -> int:
+    return int(lib().stabgpu_device_count())
+
+
+def set_host_staging(pin_mode: int = -1, copy_threads: int = 0):
+    _check(lib().stabgpu_set_host_staging(int(pin_mode), int(copy_threads)), "stabgpu_set_host_staging")
+
+
+def host_register(a: np.ndarray):
+    _check(lib().stabgpu_host_register(_ptr(a), a.nbytes), "stabgpu_host_register")
+
+
+def host_unregister(a: np.ndarray):
+    _check(lib().stabgpu_host_unregister(_ptr(a)), "stabgpu_host_unregister")
+
+
+def finalize():
+    lib().stabgpu_finalize()
 
 
 def device_info():
@@ -380,6 +417,28 @@ def temporal_polish(p: Params, vm, deta, d2eta, alpha: complex, beta: complex, s
                                          _ptr(sg), _ptr(x0c), max_iters, tol, _ptr(lam), _ptr(x), C.byref(resid), C.byref(iters)),
            "stabgpu_temporal_polish")
     return complex(lam[0]), x, resid.value, iters.value
+
+
+def polish_batch(kind: int, p: Params, vm, deta, d2eta, s1, s2, sigma, x0=None, h5=None, g2vm=None, g22vm=None, Re_pt=None,
+                 Ma_pt=None, max_iters: int = 12, tol: float = 1e-13, want_vectors: bool = True):
+    """stabgpu_polish_batch: one mode per point near sigma[p].  kind 1: A0 x = omega B0 x (s1 = alpha); kind 2:
+    (C0 + alpha C1 + alpha^2 C2) x = 0 (s1 = omega).  Returns (lambda (npts,), x (npts, n) or None, resid, iters)."""
+    vmc, g2c, g22c, de, d2e = _grid_args(p, vm, g2vm, g22vm, deta, d2eta)
+    h5c = None if h5 is None else _colmajor(_f64(h5, (p.ny, 5)))
+    a1, a2, sg = _c128(s1), _c128(s2), _c128(sigma)
+    npts, n = a1.size, NDOF * p.ny
+    assert a2.size == npts and sg.size == npts
+    re = None if Re_pt is None else _f64(Re_pt, (npts,))
+    ma = None if Ma_pt is None else _f64(Ma_pt, (npts,))
+    x0c = None if x0 is None else np.ascontiguousarray(np.asarray(x0, dtype=np.complex128).reshape(npts, n))
+    lam = np.zeros(npts, dtype=np.complex128)
+    x = np.empty((npts, n), dtype=np.complex128) if want_vectors else None
+    resid = np.zeros(npts)
+    iters = np.zeros(npts, dtype=np.int32)
+    _check(lib().stabgpu_polish_batch(kind, C.byref(p), _ptr(vmc), _ptr(g2c), _ptr(g22c), _ptr(de), _ptr(d2e), _ptr(h5c), npts,
+                                      _ptr(a1), _ptr(a2), _ptr(re), _ptr(ma), _ptr(sg), _ptr(x0c), max_iters, tol, _ptr(lam),
+                                      _ptr(x), _ptr(resid), _ptr(iters)), "stabgpu_polish_batch")
+    return lam, x, resid, iters
 
 
 def debug_stages(A: np.ndarray):

@@ -282,8 +282,13 @@ static int nint_(double v) { return (int)(v >= 0.0 ? std::floor(v + 0.5) : -std:
 
 int stabgpu_mtemporal_points(double amin, double amax, double ainc, double bmin, double bmax, double binc,
                              double* alpha_r, double* beta_r, int max_pts) {
-  int na = nint_((amax - amin) / ainc); if (na < 1) na = 1;      // mtemporal.f90:25 (no +1)
-  int nb = nint_((bmax - bmin) / binc); if (nb < 1) nb = 1;
+  // mtemporal.f90:25 divides by the increments unguarded (a zero increment is a floating exception there); here a zero
+  // or non-finite increment, or a count beyond 10^7 points, is refused with -1 instead of an undefined int conversion
+  const double qa = (amax - amin) / ainc, qb = (bmax - bmin) / binc;
+  if (!(ainc != 0.0) || !(binc != 0.0) || !std::isfinite(qa) || !std::isfinite(qb) || std::fabs(qa) > 1.0e7 || std::fabs(qb) > 1.0e7) return -1;
+  int na = nint_(qa); if (na < 1) na = 1;                          // mtemporal.f90:25 (no +1)
+  int nb = nint_(qb); if (nb < 1) nb = 1;
+  if ((long long)na * nb > 10000000LL) return -1;
   int n = 0;
   for (int ia = 1; ia <= na; ++ia)
     for (int ib = 1; ib <= nb; ++ib) {
@@ -297,7 +302,10 @@ int stabgpu_mspatial_points(double omin, double omax, double oinc, double bmin, 
                             double* omega_r, double* beta_r, int max_pts) {
   if (oinc == 0.0) oinc = 1.0;                                     // mspatial.f90:68-69
   if (binc == 0.0) binc = 1.0;
-  const int no = nint_((omax - omin) / oinc) + 1, nb = nint_((bmax - bmin) / binc) + 1;
+  const double qo = (omax - omin) / oinc, qb = (bmax - bmin) / binc;
+  if (!std::isfinite(qo) || !std::isfinite(qb) || std::fabs(qo) > 1.0e7 || std::fabs(qb) > 1.0e7) return -1;
+  const int no = nint_(qo) + 1, nb = nint_(qb) + 1;
+  if ((long long)no * nb > 10000000LL) return -1;
   int n = 0;
   for (int io = 0; io < no; ++io)
     for (int ib = 0; ib < nb; ++ib) {

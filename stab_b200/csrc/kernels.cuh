@@ -177,16 +177,6 @@ __global__ void k_lu(cplx* C, size_t cstride, int n, cplx* B, size_t bstride, in
   if (threadIdx.x == 0) info[p] = r;
 }
 
-// ---- stage 4' (north star): shift-invert polish of one mode of the pencil (A0, B0) ------------------
-__global__ void __launch_bounds__(512) k_polish(const cplx* A0, const cplx* B0, cplx* K, int n, cplx sigma, cplx* x, cplx* u, cplx* v,
-                                                int* ipiv, int max_iters, double tol, double* out4) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* red = reinterpret_cast<double*>(smem_raw);
-  cplx* sl = reinterpret_cast<cplx*>(smem_raw + 160 * sizeof(double));
-  Cta c = make_cta(red);
-  cta_polish(c, A0, B0, K, n, sigma, x, u, v, ipiv, sl, max_iters, tol, out4);
-}
-
 // ---- stage 3a: balance --------------------------------------------------------------------------
 SD_HD int balance_block(int n) { const int b = (80 * 1024) / (16 * n); return b >= 8 ? 8 : (b >= 4 ? 4 : (b >= 2 ? 2 : 1)); }   // power of two
 __global__ void __launch_bounds__(256, 2) k_balance(cplx* A, size_t astride, int n, double* scale, int* cnt, int* ilohi, int bal_b) {

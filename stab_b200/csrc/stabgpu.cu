@@ -4,20 +4,37 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/stabgpu.h"
 #include "kernels.cuh"
 #include "lu_blocked.cuh"
+#include "polish.cuh"
 
 using namespace stab;
 
 namespace {
 
 thread_local std::string g_err;
-int g_device = -1;
+int g_device = -1;            // primary device (plans, single-matrix entry points)
 int g_sm_count = 148;
 bool g_inited = false;
+
+// Devices the batch entry points shard over (stabgpu_init: one; stabgpu_init_multi: up to all of the box).  Every
+// device keeps its own cached plan and its own pinned staging ring; a batch call runs one host worker thread per device.
+struct StageRing {
+  static constexpr int NSLOT = 4;
+  size_t slot_bytes = 0;
+  char* buf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+};
+struct DevCtx { int device = 0; stabgpu_plan* cached = nullptr; StageRing ring; };
+std::vector<DevCtx> g_devs;
+int g_stage_threads = 4;      // host threads that copy one staged chunk into the caller's (pageable) array
+int g_pin_mode = 1;           // 1: pageable destinations go through the pinned staging ring; 0: plain cudaMemcpyAsync into them
 struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int hess_streams = 1; int evec_mode = 1; int lu_mode = 1; /* 1: blocked LU with DMMA updates, 0: v1 one-CTA kernel */ int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
@@ -34,7 +51,7 @@ long long* g_qrprof_dev = nullptr;
   } while (0)
 
 int ensure_init() {
-  if (g_inited) return 0;
+  if (g_inited) return cudaSetDevice(g_device) == cudaSuccess ? 0 : fail("libstabgpu: cudaSetDevice failed");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -47,6 +64,7 @@ int ensure_init() {
   if (g_device >= ndev) return fail("libstabgpu: device index out of range");
   CU(cudaSetDevice(g_device));
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, g_device) == cudaSuccess && pr.multiProcessorCount > 0) g_sm_count = pr.multiProcessorCount; }
+  if (g_devs.empty()) { DevCtx d; d.device = g_device; g_devs.push_back(d); }
   g_inited = true;
   return 0;
 }
@@ -82,6 +100,7 @@ enum Stage { ST_ASM = 0, ST_LU, ST_BAL, ST_HESS, ST_PREP, ST_QR, ST_SORT, ST_EVE
 }  // namespace
 
 struct stabgpu_plan {
+  int device = 0;          // the CUDA device that owns every buffer, stream and event of this plan
   int kind = 0;            // 1 temporal, 2 spatial, 3 generic matrices
   stabgpu_params prm;
   int ny = 0, n = 0, N = 0; // n = 5 ny, N = order of the eigenproblem (n or 2n)
@@ -92,6 +111,9 @@ struct stabgpu_plan {
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaEvent_t evSub[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double* evec_host = nullptr;            // when set (batch C-ABI calls): eigenvectors are copied to the host per sub-batch, overlapped
+  bool evec_staged = false;               // the destination is pageable: run_eigvecs only records the sub-batch events, the
+                                          // batch driver drains the vectors through the device's pinned staging ring
+  int nsub = 0, sub_m0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // sub-batch boundaries of the last eigenvector stage
   std::vector<cudaEvent_t> evA, evB;
   bool stop_after_lu = false;             // debug: assembly + LU reduce only (stabgpu_debug_spatial_reduce)
   bool prof_hess = false;                 // record events around every Hessenberg kernel class (bench breakdown)
@@ -396,10 +418,13 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
   if (sm_old > 227 * 1024) return fail("libstabgpu: matrix too large for the eigenvector kernel");
   CU(cudaFuncSetAttribute(k_evec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_old));
   const bool fast = g_tune.evec_mode == 1 && g_tune.hess_mode != 0 && N <= 1280;
-  const int nsub = !pl->evec_host ? 1 : (np >= 8 * 37 ? 8 : (np >= 4 * 37 ? 4 : (np >= 2 ? 2 : 1)));   // >= 37 matrices per sub-batch keep the kernels full
+  const bool to_host = pl->evec_host != nullptr;
+  const int nsub = !to_host ? 1 : (np >= 8 * 37 ? 8 : (np >= 4 * 37 ? 4 : (np >= 2 ? 2 : 1)));   // >= 37 matrices per sub-batch keep the kernels full
+  pl->nsub = nsub;
+  for (int sb = 0; sb <= nsub; ++sb) pl->sub_m0[sb] = (int)((long long)np * sb / nsub);
   if (hmark(pl, s, 7)) return 1;               // start marker of the eigenvector breakdown (class 7: not reported)
   for (int sb = 0; sb < nsub; ++sb) {
-    const int m0 = (int)((long long)np * sb / nsub), m1 = (int)((long long)np * (sb + 1) / nsub), cnt = m1 - m0;
+    const int m0 = pl->sub_m0[sb], m1 = pl->sub_m0[sb + 1], cnt = m1 - m0;
     if (cnt <= 0) continue;
     int chunks = 1;
     while (chunks * cnt < 2 * 148 && chunks * warps < N) chunks *= 2;
@@ -459,27 +484,28 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
         if (hmark(pl, s, 6)) return 1;
       }
     }
-    if (pl->evec_host) {                       // D2H of this sub-batch overlaps the next one
+    if (to_host) {                             // D2H of this sub-batch overlaps the next one
       if (!pl->evSub[sb]) CU(cudaEventCreateWithFlags(&pl->evSub[sb], cudaEventDisableTiming));
       CU(cudaEventRecord(pl->evSub[sb], s));
-      CU(cudaStreamWaitEvent(pl->stream2, pl->evSub[sb], 0));
-      CU(cudaMemcpyAsync(pl->evec_host + 2 * (size_t)m0 * st, pl->V.p + (size_t)m0 * st, sizeof(cplx) * (size_t)cnt * st,
-                         cudaMemcpyDeviceToHost, pl->stream2));
+      if (!pl->evec_staged) {                  // pinned destination: straight into the caller's array
+        CU(cudaStreamWaitEvent(pl->stream2, pl->evSub[sb], 0));
+        CU(cudaMemcpyAsync(pl->evec_host + 2 * (size_t)m0 * st, pl->V.p + (size_t)m0 * st, sizeof(cplx) * (size_t)cnt * st,
+                           cudaMemcpyDeviceToHost, pl->stream2));
+      }
     }
   }
-  if (pl->evec_host) {                         // the compute stream's completion covers the copies as well
+  if (to_host && !pl->evec_staged) {           // the compute stream's completion covers the copies as well
     CU(cudaEventRecord(pl->evJoin, pl->stream2));
     CU(cudaStreamWaitEvent(s, pl->evJoin, 0));
   }
   return 0;
 }
 
-// stage 2 (spatial): blocked LU reduce  A(0:n, :) <- C0^-1 A(0:n, :)  (lu_blocked.cuh)
-int run_lu_blocked(stabgpu_plan* pl) {
-  const int n = pl->n, N = pl->N, np = pl->npts;
-  cudaStream_t s = pl->stream;
-  LuBatch lb{pl->C.p, (size_t)n * n, n, pl->A.p, (size_t)N * N, N, N, pl->cnt.p, pl->lu_perm.p, pl->info_lu.p};   // ipiv lives in the balancing stage's counter array
-  CU(cudaMemsetAsync(pl->info_lu.p, 0, sizeof(int) * np, s));
+// Batched blocked LU of lb.C with the lb.nrhs right-hand-side columns riding along (lu_blocked.cuh): factor + forward
+// substitution, then the blocked back substitution.  nrhs = 0: factorization only (the polish path replays it).
+int lu_run(const LuBatch& lb, int np, cudaStream_t s, long long* launches) {
+  const int n = lb.n, N = lb.nrhs;
+  CU(cudaMemsetAsync(lb.info, 0, sizeof(int) * np, s));
   const size_t sm_trsm = sizeof(cplx) * (LU_NB * LU_TRSM_THREADS + LU_NB * LU_NB);
   const size_t sm_gemm = PipeCfg<64, 32>::smem_bytes;
   CU(cudaFuncSetAttribute(k_lu_back_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trsm));
@@ -489,32 +515,42 @@ int run_lu_blocked(stabgpu_plan* pl) {
   for (int j0 = 0; j0 < n; j0 += LU_NB) {
     const int jb = (n - j0 < LU_NB) ? n - j0 : LU_NB, r0 = j0 + jb, ncols = (n - r0) + N;
     k_lu_panel<<<np, 512, 0, s>>>(lb, j0);
-    {
+    *launches += 1;
+    if (ncols > 0) {
       int cpc = 64;                                              // columns per CTA: enough CTAs to fill the GPU, few enough to amortise the L11 load
       while (cpc > LU_SWAP_WARPS && (long long)((ncols + cpc - 1) / cpc) * np < 4LL * g_sm_count) cpc >>= 1;
       k_lu_swap_trsm_warp<<<dim3((ncols + cpc - 1) / cpc, np), LU_SWAP_WARPS * 32, 0, s>>>(lb, j0, cpc);
+      *launches += 1;
     }
-    pl->launches += 2;
     if (r0 < n) {
-      const int ti = (n - r0 + 63) / 64, tj = (N + 31) / 32;
+      const int wide = N > n - r0 ? N : n - r0;
+      const int ti = (n - r0 + 63) / 64, tj = (wide + 31) / 32;
       k_lu_gemm<0><<<gemm_grid((long long)ti * tj * 2 * np), GEMM_THREADS, sm_gemm, s>>>(lb, j0, ti, tj, 2 * np);
-      pl->launches += 1;
+      *launches += 1;
     }
     CU(cudaGetLastError());
   }
+  if (N == 0) return 0;
   const int nblk = (n + LU_NB - 1) / LU_NB;
   for (int b = nblk - 1; b >= 0; --b) {
     const int i0 = b * LU_NB, bs = (n - i0 < LU_NB) ? n - i0 : LU_NB;
     k_lu_back_trsm<<<dim3((N + LU_TRSM_THREADS - 1) / LU_TRSM_THREADS, np), LU_TRSM_THREADS, sm_trsm, s>>>(lb, i0, bs);
-    pl->launches += 1;
+    *launches += 1;
     if (i0 > 0) {
       const int ti = (i0 + 63) / 64, tj = (N + 31) / 32;
       k_lu_gemm<1><<<gemm_grid((long long)ti * tj * np), GEMM_THREADS, sm_gemm, s>>>(lb, i0, ti, tj, np);
-      pl->launches += 1;
+      *launches += 1;
     }
     CU(cudaGetLastError());
   }
   return 0;
+}
+
+// stage 2 (spatial): blocked LU reduce  A(0:n, :) <- C0^-1 A(0:n, :)
+int run_lu_blocked(stabgpu_plan* pl) {
+  const int n = pl->n, N = pl->N;
+  LuBatch lb{pl->C.p, (size_t)n * n, n, pl->A.p, (size_t)N * N, N, N, pl->cnt.p, pl->lu_perm.p, pl->info_lu.p};   // ipiv lives in the balancing stage's counter array
+  return lu_run(lb, pl->npts, pl->stream, &pl->launches);
 }
 
 // the eigen-pipeline on pl->A (npts matrices of order N): balance -> Hessenberg -> QR -> sort [-> vectors]
@@ -607,21 +643,85 @@ int check_params(const stabgpu_params* p) {
 
 }  // namespace
 
-static stabgpu_plan* g_cached = nullptr;
+namespace {
+
+void ring_release(StageRing& r) {
+  for (int i = 0; i < StageRing::NSLOT; ++i) {
+    if (r.buf[i]) cudaFreeHost(r.buf[i]);
+    if (r.ev[i]) cudaEventDestroy(r.ev[i]);
+    r.buf[i] = nullptr; r.ev[i] = nullptr;
+  }
+  r.slot_bytes = 0;
+}
+
+void release_devices() {                       // cached plans and staging rings of every device
+  for (auto& d : g_devs) {
+    cudaSetDevice(d.device);
+    if (d.cached) { stabgpu_plan* pl = d.cached; d.cached = nullptr; stabgpu_plan_destroy(pl); }
+    ring_release(d.ring);
+  }
+  g_devs.clear();
+}
+
+int use_plan(const stabgpu_plan* pl) {        // the current device is per host thread
+  CU(cudaSetDevice(pl->device));
+  return 0;
+}
+
+}  // namespace
 
 extern "C" {
 
 const char* stabgpu_last_error(void) { return g_err.c_str(); }
 
 int stabgpu_init(int device) {
+  if (g_inited) release_devices();             // a cached plan lives on the device it was created on
   g_inited = false;
   g_device = device;
   return ensure_init();
 }
 
+int stabgpu_init_multi(int max_devices, int* ndev_used) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("libstabgpu: no CUDA device available (there is no CPU fallback for the hot path)");
+  if (max_devices > 0 && max_devices < ndev) ndev = max_devices;
+  if (g_inited) release_devices();
+  g_inited = false;
+  g_device = 0;
+  if (ensure_init()) return 1;
+  g_devs.clear();
+  for (int d = 0; d < ndev; ++d) { DevCtx c; c.device = d; g_devs.push_back(c); }
+  if (ndev_used) *ndev_used = ndev;
+  return 0;
+}
+
+int stabgpu_device_count(void) { return g_inited ? (int)g_devs.size() : 0; }
+
+int stabgpu_set_host_staging(int pin_mode, int copy_threads) {
+  if (pin_mode == 0 || pin_mode == 1) g_pin_mode = pin_mode;
+  if (copy_threads > 0) g_stage_threads = copy_threads > 32 ? 32 : copy_threads;
+  return 0;
+}
+
+/* page-lock a caller array once (e.g. the Fortran evec array after its allocate) so that the batch calls copy into it
+ * directly; the staging ring is used for any destination that is not page-locked */
+int stabgpu_host_register(void* ptr, size_t bytes) {
+  if (ensure_init()) return 1;
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int stabgpu_host_unregister(void* ptr) {
+  CU(cudaHostUnregister(ptr));
+  return 0;
+}
+
 int stabgpu_finalize(void) {
-  if (g_cached) { stabgpu_plan_destroy(g_cached); g_cached = nullptr; }
-  if (g_inited) cudaDeviceSynchronize();
+  if (g_inited) {
+    for (auto& d : g_devs) { cudaSetDevice(d.device); cudaDeviceSynchronize(); }
+    release_devices();
+    cudaSetDevice(g_device);
+  }
   g_inited = false;
   return 0;
 }
@@ -656,23 +756,37 @@ int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_th
   return 0;
 }
 
-int stabgpu_plan_create(stabgpu_plan** out, int kind, const stabgpu_params* p, const double* vm, const double* g2vm,
-                        const double* g22vm, const double* deta, const double* d2eta, const double* h5, int max_pts,
-                        int want_vectors) {
-  if (ensure_init()) return 1;
+// plan on the calling thread's CURRENT device (the batch workers set their own before they get here)
+static int plan_create_here(stabgpu_plan** out, int kind, const stabgpu_params* p, const double* vm, const double* g2vm,
+                            const double* g22vm, const double* deta, const double* d2eta, const double* h5, int max_pts,
+                            int want_vectors) {
   if (kind != 1 && kind != 2) return fail("libstabgpu: plan kind must be 1 (temporal) or 2 (spatial)");
   if (check_params(p)) return 1;
   if (!vm || !deta || !d2eta || max_pts < 1) return fail("libstabgpu: bad argument");
   stabgpu_plan* pl = new stabgpu_plan();
+  CU(cudaGetDevice(&pl->device));              // the calling thread's current device (a batch worker sets its own)
   pl->kind = kind; pl->prm = *p; pl->ny = p->ny; pl->n = 5 * p->ny; pl->N = (kind == 1 ? 1 : 2) * pl->n;
   pl->want_vectors = want_vectors ? 1 : 0;
-  if (upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, h5) || plan_alloc(pl, max_pts)) { delete pl; return 1; }
+  if (upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, h5) || plan_alloc(pl, max_pts)) {
+    const std::string keep = g_err;
+    stabgpu_plan_destroy(pl);                  // frees the streams and events plan_alloc may already have created
+    g_err = keep;
+    return 1;
+  }
   *out = pl;
   return 0;
 }
 
+int stabgpu_plan_create(stabgpu_plan** out, int kind, const stabgpu_params* p, const double* vm, const double* g2vm,
+                        const double* g22vm, const double* deta, const double* d2eta, const double* h5, int max_pts,
+                        int want_vectors) {
+  if (ensure_init()) return 1;                 // selects the primary device for this thread
+  return plan_create_here(out, kind, p, vm, g2vm, g22vm, deta, d2eta, h5, max_pts, want_vectors);
+}
+
 int stabgpu_plan_upload(stabgpu_plan* pl, int npts, const double* s1, const double* s2, const double* Re_pt, const double* Ma_pt) {
   if (!pl || npts < 1 || npts > pl->cap || !s1 || !s2) return fail("libstabgpu: plan_upload bad argument");
+  if (use_plan(pl)) return 1;
   pl->npts = npts;
   CU(cudaMemcpyAsync(pl->s1.p, s1, sizeof(cplx) * npts, cudaMemcpyHostToDevice, pl->stream));
   CU(cudaMemcpyAsync(pl->s2.p, s2, sizeof(cplx) * npts, cudaMemcpyHostToDevice, pl->stream));
@@ -685,6 +799,7 @@ int stabgpu_plan_upload(stabgpu_plan* pl, int npts, const double* s1, const doub
 
 int stabgpu_plan_enqueue(stabgpu_plan* pl) {
   if (!pl || pl->npts < 1) return fail("libstabgpu: plan_execute without uploaded points");
+  if (use_plan(pl)) return 1;
   const int np = pl->npts, ny = pl->ny, n = pl->n, N = pl->N;
   cudaStream_t s = pl->stream;
   pl->launches = 0;
@@ -728,6 +843,7 @@ int stabgpu_plan_enqueue(stabgpu_plan* pl) {
 
 int stabgpu_plan_wait(stabgpu_plan* pl) {
   if (!pl) return fail("libstabgpu: null plan");
+  if (use_plan(pl)) return 1;
   CU(cudaStreamSynchronize(pl->stream));
   if (pl->prof_hess && pl->pev_n > 1) {
     for (int c = 0; c < 8; ++c) pl->hess_ms[c] = 0.f;
@@ -752,6 +868,7 @@ int stabgpu_plan_execute(stabgpu_plan* pl) {
 
 int stabgpu_plan_download(stabgpu_plan* pl, double* eig, double* evec, int* info) {
   if (!pl || pl->npts < 1) return fail("libstabgpu: plan_download without results");
+  if (use_plan(pl)) return 1;
   const int np = pl->npts, N = pl->N;
   if (eig) CU(cudaMemcpy(eig, pl->eig.p, sizeof(cplx) * (size_t)np * N, cudaMemcpyDeviceToHost));
   if (evec) {
@@ -794,6 +911,7 @@ int stabgpu_plan_profile_hessenberg(stabgpu_plan* pl, int enable, float* ms4) {
 
 int stabgpu_plan_ilohi(stabgpu_plan* pl, int* ilohi) {
   if (!pl || pl->npts < 1 || !ilohi) return fail("libstabgpu: plan_ilohi bad argument");
+  if (use_plan(pl)) return 1;
   CU(cudaMemcpy(ilohi, pl->ilohi.p, sizeof(int) * 2 * pl->npts, cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -802,7 +920,9 @@ void* stabgpu_plan_eig_dev(stabgpu_plan* pl) { return pl ? (void*)pl->eig.p : nu
 
 int stabgpu_plan_destroy(stabgpu_plan* pl) {
   if (!pl) return 0;
-  if (pl == g_cached) g_cached = nullptr;
+  for (auto& d : g_devs) if (d.cached == pl) d.cached = nullptr;
+  int prev = 0;
+  const bool switched = cudaGetDevice(&prev) == cudaSuccess && prev != pl->device && cudaSetDevice(pl->device) == cudaSuccess;
   if (pl->stream) cudaStreamDestroy(pl->stream);
   if (pl->stream2) cudaStreamDestroy(pl->stream2);
   if (pl->evFork) cudaEventDestroy(pl->evFork);
@@ -812,12 +932,150 @@ int stabgpu_plan_destroy(stabgpu_plan* pl) {
   for (auto e : pl->evB) cudaEventDestroy(e);
   for (auto e : pl->pev) cudaEventDestroy(e);
   for (int i = 0; i <= ST_N; ++i) if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
-  delete pl;
+  delete pl;                                   // DBuf members: cudaFree on the owning device
+  if (switched) cudaSetDevice(prev);
   return 0;
 }
 
-// The batch entry points keep ONE plan (device workspace) alive between calls: a sweep driver calls
+// The batch entry points keep ONE plan (device workspace) per device alive between calls: a sweep driver calls
 // them repeatedly with the same problem shape, and cudaMalloc of GBs per call would dominate.
+
+}  // extern "C"
+
+namespace {
+
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  const int nt = (bytes < ((size_t)4 << 20)) ? 1 : g_stage_threads;
+  if (nt <= 1) { std::memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;
+  for (int i = 1; i < nt; ++i) {
+    const size_t off = (size_t)i * part;
+    if (off >= bytes) break;
+    const size_t len = std::min(part, bytes - off);
+    th.emplace_back([=] { std::memcpy((char*)dst + off, (const char*)src + off, len); });
+  }
+  std::memcpy(dst, src, std::min(part, bytes));
+  for (auto& t : th) t.join();
+}
+
+int ring_ensure(StageRing& r, size_t want) {
+  if (r.slot_bytes >= want) return 0;
+  ring_release(r);
+  for (int i = 0; i < StageRing::NSLOT; ++i) {
+    CU(cudaHostAlloc((void**)&r.buf[i], want, cudaHostAllocPortable));
+    CU(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming));
+  }
+  r.slot_bytes = want;
+  return 0;
+}
+
+// Pageable destination: the vectors of each finished sub-batch travel device -> pinned ring slot (DMA, copy stream) ->
+// caller array (host threads).  Up to NSLOT-1 chunks are in flight on the copy engine while one is copied out, and all of
+// it runs under the kernels of the later sub-batches, which are already enqueued on the compute stream.
+int drain_vectors_staged(stabgpu_plan* pl, StageRing& ring, double* dst_host) {
+  const size_t st = (size_t)pl->N * pl->N, mat_bytes = st * sizeof(cplx);
+  size_t per = ((size_t)64 << 20) / mat_bytes; if (per < 1) per = 1;
+  if (ring_ensure(ring, per * mat_bytes)) return 1;
+  struct Pend { char* dst; size_t bytes; bool live; } pend[StageRing::NSLOT] = {};
+  auto finish = [&](int slot) -> int {
+    if (!pend[slot].live) return 0;
+    CU(cudaEventSynchronize(ring.ev[slot]));
+    parallel_memcpy(pend[slot].dst, ring.buf[slot], pend[slot].bytes);
+    pend[slot].live = false;
+    return 0;
+  };
+  long long k = 0;
+  for (int sb = 0; sb < pl->nsub; ++sb) {
+    const int m0 = pl->sub_m0[sb], m1 = pl->sub_m0[sb + 1];
+    if (m1 <= m0) continue;
+    CU(cudaStreamWaitEvent(pl->stream2, pl->evSub[sb], 0));
+    for (int m = m0; m < m1; m += (int)per, ++k) {
+      const int slot = (int)(k % StageRing::NSLOT);
+      if (finish(slot)) return 1;
+      const int cnt = std::min((int)per, m1 - m);
+      CU(cudaMemcpyAsync(ring.buf[slot], pl->V.p + (size_t)m * st, (size_t)cnt * mat_bytes, cudaMemcpyDeviceToHost, pl->stream2));
+      CU(cudaEventRecord(ring.ev[slot], pl->stream2));
+      pend[slot].dst = (char*)dst_host + (size_t)m * mat_bytes; pend[slot].bytes = (size_t)cnt * mat_bytes; pend[slot].live = true;
+    }
+  }
+  for (long long q = k; q < k + StageRing::NSLOT; ++q) if (finish((int)(q % StageRing::NSLOT))) return 1;
+  return 0;
+}
+
+bool host_is_pinned(const void* ptr) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+struct BatchArgs {
+  int kind; const stabgpu_params* p; const double *vm, *g2vm, *g22vm, *deta, *d2eta, *h5;
+  const double *s1, *s2, *Re_pt, *Ma_pt; int want_vectors; double *eig, *evec; int* info; bool evec_pinned;
+};
+
+// points [lo, hi) of the call on device slot `slot`; runs on its own host thread when the call is sharded
+int batch_on_device(int slot, const BatchArgs& a, int lo, int hi) {
+  DevCtx& dc = g_devs[slot];
+  CU(cudaSetDevice(dc.device));
+  const int npts = hi - lo, want_vectors = a.want_vectors;
+  stabgpu_plan* pl = dc.cached;
+  if (pl && (pl->kind != a.kind || pl->ny != a.p->ny || pl->want_vectors != (want_vectors ? 1 : 0) || (pl->cap < npts && !pl->cap_limited))) {
+    dc.cached = nullptr;
+    stabgpu_plan_destroy(pl);
+    pl = nullptr;
+  }
+  if (!pl) {
+    if (plan_create_here(&pl, a.kind, a.p, a.vm, a.g2vm, a.g22vm, a.deta, a.d2eta, a.h5, npts, want_vectors)) return 1;
+    dc.cached = pl;
+  } else {
+    pl->prm = *a.p;
+    if (upload_grid(pl, a.p, a.vm, a.g2vm, a.g22vm, a.deta, a.d2eta, a.h5)) return 1;
+  }
+  const int N = pl->N;
+  const bool staged = want_vectors && !a.evec_pinned && g_pin_mode == 1;
+  int rc = 0;
+  for (int p0 = lo; p0 < hi && !rc; p0 += pl->cap) {
+    int m = hi - p0; if (m > pl->cap) m = pl->cap;
+    rc = stabgpu_plan_upload(pl, m, a.s1 + 2 * (size_t)p0, a.s2 + 2 * (size_t)p0, a.Re_pt ? a.Re_pt + p0 : nullptr, a.Ma_pt ? a.Ma_pt + p0 : nullptr);
+    double* dst = want_vectors ? a.evec + 2 * (size_t)p0 * N * N : nullptr;
+    pl->evec_host = dst;                       // D2H of the vectors overlaps the eigenvector stage
+    pl->evec_staged = staged;
+    if (!rc) rc = stabgpu_plan_enqueue(pl);
+    if (!rc && staged) rc = drain_vectors_staged(pl, dc.ring, dst);
+    if (!rc) rc = stabgpu_plan_wait(pl);
+    pl->evec_host = nullptr; pl->evec_staged = false;
+    if (!rc) rc = stabgpu_plan_download(pl, a.eig + 2 * (size_t)p0 * N, nullptr, a.info ? a.info + p0 : nullptr);
+  }
+  return rc;
+}
+
+// run fn(slot, lo, hi) for the contiguous shards of stabgpu_shard_range on the devices of g_devs, one host thread per
+// device (slot 0 on the calling thread); the first error message is handed to the caller's stabgpu_last_error()
+template <class F>
+int shard_over_devices(int npts, F fn) {
+  const int ndev = (int)g_devs.size() < npts ? (int)g_devs.size() : npts;
+  if (ndev <= 1) { const int rc = fn(0, 0, npts); cudaSetDevice(g_device); return rc; }
+  std::vector<int> rcs(ndev, 0);
+  std::vector<std::string> errs(ndev);
+  std::vector<std::thread> th;
+  auto work = [&](int d) {
+    int lo = 0, hi = 0;
+    stabgpu_shard_range(npts, d, ndev, &lo, &hi);
+    g_err.clear();
+    rcs[d] = hi > lo ? fn(d, lo, hi) : 0;
+    if (rcs[d]) errs[d] = g_err;
+  };
+  for (int d = 1; d < ndev; ++d) th.emplace_back(work, d);
+  work(0);
+  for (auto& t : th) t.join();
+  cudaSetDevice(g_device);
+  for (int d = 0; d < ndev; ++d)
+    if (rcs[d]) return fail("device " + std::to_string(g_devs[d].device) + ": " + errs[d]);
+  return 0;
+}
+
+}  // namespace
 
 static int batch_common(int kind, const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
                         const double* deta, const double* d2eta, const double* h5, int npts, const double* s1,
@@ -827,29 +1085,104 @@ static int batch_common(int kind, const stabgpu_params* p, const double* vm, con
   if (want_vectors && !evec) return fail("libstabgpu: want_vectors set but evec is NULL");
   if (ensure_init()) return 1;
   if (check_params(p)) return 1;
-  stabgpu_plan* pl = g_cached;
-  if (pl && (pl->kind != kind || pl->ny != p->ny || pl->want_vectors != (want_vectors ? 1 : 0) || (pl->cap < npts && !pl->cap_limited))) {
-    stabgpu_plan_destroy(pl);
-    pl = g_cached = nullptr;
+  if (!vm || !deta || !d2eta) return fail("libstabgpu: bad argument");
+  BatchArgs a{kind, p, vm, g2vm, g22vm, deta, d2eta, h5, s1, s2, Re_pt, Ma_pt, want_vectors, eig, evec, info,
+              want_vectors ? host_is_pinned(evec) : true};
+  return shard_over_devices(npts, [&](int slot, int lo, int hi) { return batch_on_device(slot, a, lo, hi); });
+}
+
+// Batched polish (polish.cuh) of the points [lo, hi) on device slot `slot`
+struct PolishArgs {
+  int kind; const stabgpu_params* p; const double *vm, *g2vm, *g22vm, *deta, *d2eta, *h5;
+  const double *s1, *s2, *Re_pt, *Ma_pt, *sigma, *x0; int max_iters; double tol;
+  double *lambda, *x, *resid; int* iters;
+};
+
+static int polish_on_device(int slot, const PolishArgs& a, int lo, int hi) {
+  CU(cudaSetDevice(g_devs[slot].device));
+  const stabgpu_params* p = a.p;
+  const int ny = p->ny, n = 5 * ny, kind = a.kind;
+  const size_t st = (size_t)n * n;
+  stabgpu_plan* pl = new stabgpu_plan();       // grid / profile holder only
+  CU(cudaGetDevice(&pl->device));
+  pl->kind = kind; pl->prm = *p; pl->ny = ny; pl->n = n; pl->N = n;
+  struct Guard { stabgpu_plan* pl; ~Guard() { stabgpu_plan_destroy(pl); } } guard{pl};
+  if (upload_grid(pl, p, a.vm, a.g2vm, a.g22vm, a.deta, a.d2eta, a.h5)) return 1;
+  size_t freeb = 0, totalb = 0;
+  CU(cudaMemGetInfo(&freeb, &totalb));
+  const size_t per_pt = ((kind == 2 ? 4 : 3) * st + (size_t)ny * 175 + 3 * (size_t)n) * sizeof(cplx) + 4096;
+  int cap = (int)std::min<size_t>((size_t)(hi - lo), (size_t)(0.8 * (double)freeb) / per_pt);
+  if (cap < 1) return fail("libstabgpu: not enough device memory to polish a single point");
+  DBuf<cplx> coef, blk, M0, M1, M2, K, sv1, sv2, sg, xv, dummy;
+  DBuf<double> Re, Ma, out4;
+  DBuf<int> ipiv, perm, info;
+  if (coef.alloc((size_t)cap * ny * (kind == 1 ? 75 : 150)) || (kind == 1 && blk.alloc((size_t)cap * ny * 25)) || M0.alloc(cap * st) ||
+      M1.alloc(cap * st) || (kind == 2 && M2.alloc(cap * st)) || K.alloc(cap * st) || sv1.alloc(cap) || sv2.alloc(cap) || sg.alloc(cap) ||
+      xv.alloc((size_t)cap * n) || dummy.alloc(16) || Re.alloc(cap) || Ma.alloc(cap) || out4.alloc((size_t)cap * 4) ||
+      ipiv.alloc((size_t)cap * n) || perm.alloc((size_t)cap * LU_PERM) || info.alloc(cap)) return 1;
+  cudaStream_t s = nullptr;
+  CU(cudaStreamCreate(&s));
+  struct SGuard { cudaStream_t s; ~SGuard() { cudaStreamDestroy(s); } } sguard{s};
+  const size_t smem = 160 * sizeof(double) + 4 * (size_t)n * sizeof(cplx);
+  CU(cudaFuncSetAttribute(k_polish_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GridDev g = pl->grid();
+  Phys ph = phys_from(p);
+  std::vector<cplx> xh;
+  std::vector<double> oh;
+  long long launches = 0;
+  for (int p0 = lo; p0 < hi; p0 += cap) {
+    const int m = std::min(cap, hi - p0);
+    CU(cudaMemcpyAsync(sv1.p, a.s1 + 2 * (size_t)p0, sizeof(cplx) * m, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(sv2.p, a.s2 + 2 * (size_t)p0, sizeof(cplx) * m, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(sg.p, a.sigma + 2 * (size_t)p0, sizeof(cplx) * m, cudaMemcpyHostToDevice, s));
+    if (a.Re_pt) CU(cudaMemcpyAsync(Re.p, a.Re_pt + p0, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    if (a.Ma_pt) CU(cudaMemcpyAsync(Ma.p, a.Ma_pt + p0, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    if (a.x0) {
+      CU(cudaMemcpyAsync(xv.p, a.x0 + 2 * (size_t)p0 * n, sizeof(cplx) * (size_t)m * n, cudaMemcpyHostToDevice, s));
+    } else {
+      xh.assign((size_t)m * n, mk(1.0, 0.0));
+      CU(cudaMemcpyAsync(xv.p, xh.data(), sizeof(cplx) * (size_t)m * n, cudaMemcpyHostToDevice, s));
+    }
+    SweepDev sw; sw.s1 = sv1.p; sw.s2 = sv2.p; sw.Re = a.Re_pt ? Re.p : nullptr; sw.Ma = a.Ma_pt ? Ma.p : nullptr;
+    dim3 cgrid((ny + 63) / 64, m);
+    if (kind == 1) k_node_coef_temporal<<<cgrid, 64, 0, s>>>(g, ph, sw, 0, 0, coef.p, blk.p);
+    else k_node_coef_spatial<<<cgrid, 64, 0, s>>>(g, ph, sw, 0, coef.p);
+    CU(cudaGetLastError());
+    LuBatch lb{K.p, st, n, dummy.p, 0, n, 0, ipiv.p, perm.p, info.p};
+    PolishBatch pb{n, kind, M0.p, M1.p, M2.p, K.p, st, ipiv.p, info.p, sg.p, xv.p, out4.p};
+    k_polish_form<<<dim3((unsigned)((st + 255) / 256), m), 256, 0, s>>>(g, coef.p, blk.p, pb);
+    CU(cudaGetLastError());
+    if (lu_run(lb, m, s, &launches)) return 1;
+    k_polish_iterate<<<m, 512, smem, s>>>(pb, a.max_iters, a.tol);
+    CU(cudaGetLastError());
+    oh.resize((size_t)m * 4);
+    CU(cudaMemcpyAsync(oh.data(), out4.p, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s));
+    if (a.x) CU(cudaMemcpyAsync(a.x + 2 * (size_t)p0 * n, xv.p, sizeof(cplx) * (size_t)m * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int k = 0; k < m; ++k) {
+      a.lambda[2 * (size_t)(p0 + k)] = oh[4 * k]; a.lambda[2 * (size_t)(p0 + k) + 1] = oh[4 * k + 1];
+      if (a.resid) a.resid[p0 + k] = oh[4 * k + 2];
+      if (a.iters) a.iters[p0 + k] = (int)oh[4 * k + 3];
+    }
   }
-  if (!pl) {
-    if (stabgpu_plan_create(&pl, kind, p, vm, g2vm, g22vm, deta, d2eta, h5, npts, want_vectors)) return 1;
-    g_cached = pl;
-  } else {
-    pl->prm = *p;
-    if (upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, h5)) return 1;
-  }
-  const int N = pl->N;
-  int rc = 0;
-  for (int p0 = 0; p0 < npts && !rc; p0 += pl->cap) {
-    int m = npts - p0; if (m > pl->cap) m = pl->cap;
-    rc = stabgpu_plan_upload(pl, m, s1 + 2 * (size_t)p0, s2 + 2 * (size_t)p0, Re_pt ? Re_pt + p0 : nullptr, Ma_pt ? Ma_pt + p0 : nullptr);
-    pl->evec_host = want_vectors ? evec + 2 * (size_t)p0 * N * N : nullptr;   // D2H of the vectors overlaps the eigenvector stage
-    if (!rc) rc = stabgpu_plan_execute(pl);
-    pl->evec_host = nullptr;
-    if (!rc) rc = stabgpu_plan_download(pl, eig + 2 * (size_t)p0 * N, nullptr, info ? info + p0 : nullptr);
-  }
-  return rc;
+  return 0;
+}
+
+extern "C" {
+
+/* Stage (4) of the north star, batched over sweep points: see polish.cuh and include/stabgpu.h */
+int stabgpu_polish_batch(int kind, const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
+                         const double* deta, const double* d2eta, const double* h5, int npts, const double* s1,
+                         const double* s2, const double* Re_pt, const double* Ma_pt, const double* sigma, const double* x0,
+                         int max_iters, double tol, double* lambda, double* x, double* resid, int* iters) {
+  if (kind != 1 && kind != 2) return fail("libstabgpu: polish kind must be 1 (temporal) or 2 (spatial)");
+  if (npts < 1 || !vm || !deta || !d2eta || !s1 || !s2 || !sigma || !lambda) return fail("libstabgpu: polish bad argument");
+  if (ensure_init()) return 1;
+  if (check_params(p)) return 1;
+  if (5 * p->ny > 1280) return fail("libstabgpu: polish supports ny <= 256");
+  PolishArgs a{kind, p, vm, g2vm, g22vm, deta, d2eta, kind == 2 ? h5 : nullptr, s1, s2, Re_pt, Ma_pt, sigma, x0,
+               max_iters < 1 ? 12 : max_iters, tol <= 0.0 ? 1e-13 : tol, lambda, x, resid, iters};
+  return shard_over_devices(npts, [&](int slot, int lo, int hi) { return polish_on_device(slot, a, lo, hi); });
 }
 
 int stabgpu_temporal_batch(const stabgpu_params* p, const double* vm, const double* g2vm, const double* g22vm,
@@ -878,6 +1211,7 @@ int stabgpu_zgeev_batch(int n, int batch, const double* A, int want_vectors, dou
     return 0;
   }
   stabgpu_plan* pl = new stabgpu_plan();
+  cudaGetDevice(&pl->device);
   pl->kind = 3; pl->ny = 0; pl->n = n; pl->N = n; pl->want_vectors = want_vectors ? 1 : 0;
   int rc = plan_alloc(pl, batch);
   for (int p0 = 0; p0 < batch && !rc; p0 += pl->cap) {
@@ -907,34 +1241,35 @@ int stabgpu_zgeev_batch(int n, int batch, const double* A, int want_vectors, dou
 
 int stabgpu_debug_stages(int n, const double* A, double* balanced, double* scale, int* ilo, int* ihi, double* hess, double* tau) {
   if (ensure_init()) return 1;
+  if (n < 1 || !A) return fail("libstabgpu: bad argument");
   stabgpu_plan* pl = new stabgpu_plan();
+  struct Guard { stabgpu_plan* pl; ~Guard() { stabgpu_plan_destroy(pl); } } guard{pl};
+  CU(cudaGetDevice(&pl->device));
   pl->kind = 3; pl->n = n; pl->N = n; pl->want_vectors = 0;
-  int rc = plan_alloc(pl, 1);
-  if (rc) { stabgpu_plan_destroy(pl); return 1; }
+  if (plan_alloc(pl, 1)) return 1;
   const size_t st = (size_t)n * n;
   cudaStream_t s = pl->stream;
-  cudaMemcpy(pl->A.p, A, sizeof(cplx) * st, cudaMemcpyHostToDevice);
+  CU(cudaMemcpy(pl->A.p, A, sizeof(cplx) * st, cudaMemcpyHostToDevice));
   {
     const int bb = balance_block(n);
     const size_t smb = balance_wsp_doubles(n, bb) * sizeof(double);
-    cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    CU(cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
     k_balance<<<1, 256, smb, s>>>(pl->A.p, st, n, pl->scale.p, pl->cnt.p, pl->ilohi.p, bb);
+    CU(cudaGetLastError());
   }
-  cudaStreamSynchronize(s);
+  CU(cudaStreamSynchronize(s));
   int lh[2];
-  cudaMemcpy(lh, pl->ilohi.p, sizeof(lh), cudaMemcpyDeviceToHost);
+  CU(cudaMemcpy(lh, pl->ilohi.p, sizeof(lh), cudaMemcpyDeviceToHost));
   if (ilo) *ilo = lh[0];
   if (ihi) *ihi = lh[1];
-  if (balanced) cudaMemcpy(balanced, pl->A.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
-  if (scale) cudaMemcpy(scale, pl->scale.p, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  if (balanced) CU(cudaMemcpy(balanced, pl->A.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost));
+  if (scale) CU(cudaMemcpy(scale, pl->scale.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
   pl->npts = 1;
-  if (run_hessenberg(pl)) { stabgpu_plan_destroy(pl); return 1; }
-  cudaStreamSynchronize(s);
-  if (hess) cudaMemcpy(hess, pl->A.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
-  if (tau) cudaMemcpy(tau, pl->tau.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost);
-  cudaError_t e = cudaGetLastError();
-  stabgpu_plan_destroy(pl);
-  if (e != cudaSuccess) return fail(std::string("libstabgpu: ") + cudaGetErrorString(e));
+  if (run_hessenberg(pl)) return 1;
+  CU(cudaStreamSynchronize(s));
+  if (hess) CU(cudaMemcpy(hess, pl->A.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost));
+  if (tau) CU(cudaMemcpy(tau, pl->tau.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost));
+  CU(cudaGetLastError());
   return 0;
 }
 
@@ -943,16 +1278,18 @@ static int inspect_common(int kind, const stabgpu_params* p, const double* vm, c
                           double* o0, double* o1, double* o2) {
   if (ensure_init()) return 1;
   if (check_params(p)) return 1;
+  if (!vm || !deta || !d2eta || !s1 || !s2 || !o0 || !o1) return fail("libstabgpu: bad argument");
   stabgpu_plan* pl = new stabgpu_plan();
+  struct Guard { stabgpu_plan* pl; ~Guard() { stabgpu_plan_destroy(pl); } } guard{pl};
+  CU(cudaGetDevice(&pl->device));
   pl->kind = kind; pl->prm = *p; pl->ny = p->ny; pl->n = 5 * p->ny; pl->N = pl->n; pl->want_vectors = 0;
-  int rc = upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, h5);
+  if (upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, h5)) return 1;
   const int ny = p->ny, n = pl->n;
   const size_t st = (size_t)n * n;
   DBuf<cplx> coef, blk, m0, m1, m2, sv1, sv2;
-  if (!rc) rc = coef.alloc((size_t)ny * 150) || blk.alloc((size_t)ny * 25) || m0.alloc(st) || m1.alloc(st) || m2.alloc(st) || sv1.alloc(1) || sv2.alloc(1);
-  if (rc) { stabgpu_plan_destroy(pl); return 1; }
-  cudaMemcpy(sv1.p, s1, sizeof(cplx), cudaMemcpyHostToDevice);
-  cudaMemcpy(sv2.p, s2, sizeof(cplx), cudaMemcpyHostToDevice);
+  if (coef.alloc((size_t)ny * 150) || blk.alloc((size_t)ny * 25) || m0.alloc(st) || m1.alloc(st) || m2.alloc(st) || sv1.alloc(1) || sv2.alloc(1)) return 1;
+  CU(cudaMemcpy(sv1.p, s1, sizeof(cplx), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(sv2.p, s2, sizeof(cplx), cudaMemcpyHostToDevice));
   GridDev g = pl->grid();
   Phys ph = phys_from(p);
   SweepDev sw; sw.s1 = sv1.p; sw.s2 = sv2.p; sw.Re = nullptr; sw.Ma = nullptr;
@@ -960,20 +1297,18 @@ static int inspect_common(int kind, const stabgpu_params* p, const double* vm, c
   const int eb = (int)((st + 255) / 256);
   if (kind == 1) {
     k_node_coef_temporal<<<cgrid, 64>>>(g, ph, sw, 0, 0, coef.p, blk.p);
+    CU(cudaGetLastError());
     k_inspect_temporal<<<eb, 256>>>(g, coef.p, blk.p, m0.p, m1.p);
   } else {
     k_node_coef_spatial<<<cgrid, 64>>>(g, ph, sw, 0, coef.p);
+    CU(cudaGetLastError());
     k_inspect_spatial<<<eb, 256>>>(g, coef.p, m0.p, m1.p, m2.p);
   }
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) {
-    cudaMemcpy(o0, m0.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
-    cudaMemcpy(o1, m1.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
-    if (o2) cudaMemcpy(o2, m2.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost);
-    e = cudaGetLastError();
-  }
-  stabgpu_plan_destroy(pl);
-  if (e != cudaSuccess) return fail(std::string("libstabgpu: ") + cudaGetErrorString(e));
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(o0, m0.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(o1, m1.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost));
+  if (o2) CU(cudaMemcpy(o2, m2.p, sizeof(cplx) * st, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1011,48 +1346,12 @@ int stabgpu_temporal_polish(const stabgpu_params* p, const double* vm, const dou
                             const double* deta, const double* d2eta, const double* alpha, const double* beta,
                             const double* sigma, const double* x0, int max_iters, double tol, double* lambda, double* x,
                             double* resid, int* iters) {
-  if (ensure_init()) return 1;
-  if (check_params(p)) return 1;
-  if (!vm || !deta || !d2eta || !alpha || !beta || !sigma || !lambda) return fail("libstabgpu: polish bad argument");
-  if (max_iters < 1) max_iters = 8;
-  if (tol <= 0.0) tol = 1e-13;
-  stabgpu_plan* pl = new stabgpu_plan();
-  pl->kind = 1; pl->prm = *p; pl->ny = p->ny; pl->n = 5 * p->ny; pl->N = pl->n; pl->want_vectors = 0;
-  int rc = upload_grid(pl, p, vm, g2vm, g22vm, deta, d2eta, nullptr);
-  const int ny = p->ny, n = pl->n;
-  const size_t st = (size_t)n * n;
-  DBuf<cplx> coef, blk, A0, B0, K, sv1, sv2, xv, uv, vv;
-  DBuf<int> ipiv;
-  DBuf<double> out4;
-  if (!rc) rc = coef.alloc((size_t)ny * 75) || blk.alloc((size_t)ny * 25) || A0.alloc(st) || B0.alloc(st) || K.alloc(st) || sv1.alloc(1) ||
-                sv2.alloc(1) || xv.alloc(n) || uv.alloc(n) || vv.alloc(n) || ipiv.alloc(n) || out4.alloc(4);
-  if (rc) { stabgpu_plan_destroy(pl); return 1; }
-  cudaMemcpy(sv1.p, alpha, sizeof(cplx), cudaMemcpyHostToDevice);
-  cudaMemcpy(sv2.p, beta, sizeof(cplx), cudaMemcpyHostToDevice);
-  std::vector<cplx> xh(n);
-  for (int i = 0; i < n; ++i) xh[i] = x0 ? mk(x0[2 * i], x0[2 * i + 1]) : mk(1.0, 0.0);
-  cudaMemcpy(xv.p, xh.data(), sizeof(cplx) * n, cudaMemcpyHostToDevice);
-  GridDev g = pl->grid();
-  Phys ph = phys_from(p);
-  SweepDev sw; sw.s1 = sv1.p; sw.s2 = sv2.p; sw.Re = nullptr; sw.Ma = nullptr;
-  k_node_coef_temporal<<<dim3((ny + 63) / 64, 1), 64>>>(g, ph, sw, 0, 0, coef.p, blk.p);
-  k_inspect_temporal<<<(int)((st + 255) / 256), 256>>>(g, coef.p, blk.p, A0.p, B0.p);
-  const size_t sm = 160 * sizeof(double) + (size_t)n * sizeof(cplx);
-  cudaFuncSetAttribute(k_polish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_polish<<<1, 512, sm>>>(A0.p, B0.p, K.p, n, mk(sigma[0], sigma[1]), xv.p, uv.p, vv.p, ipiv.p, max_iters, tol, out4.p);
-  cudaError_t e = cudaDeviceSynchronize();
-  double o[4] = {0, 0, 0, 0};
-  if (e == cudaSuccess) {
-    cudaMemcpy(o, out4.p, sizeof(o), cudaMemcpyDeviceToHost);
-    if (x) cudaMemcpy(x, xv.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost);
-    e = cudaGetLastError();
-  }
-  stabgpu_plan_destroy(pl);
-  if (e != cudaSuccess) return fail(std::string("libstabgpu: ") + cudaGetErrorString(e));
-  lambda[0] = o[0]; lambda[1] = o[1];
-  if (resid) *resid = o[2];
-  if (iters) *iters = (int)o[3];
-  if (o[3] < 0) return fail("libstabgpu: polish: A0 - sigma B0 is exactly singular (sigma is an eigenvalue to working precision; perturb it)");
+  if (!alpha || !beta || !sigma || !lambda) return fail("libstabgpu: polish bad argument");
+  int it = 0;
+  if (stabgpu_polish_batch(1, p, vm, g2vm, g22vm, deta, d2eta, nullptr, 1, alpha, beta, nullptr, nullptr, sigma, x0,
+                           max_iters < 1 ? 8 : max_iters, tol, lambda, x, resid, &it)) return 1;
+  if (iters) *iters = it;
+  if (it < 0) return fail("libstabgpu: polish: A0 - sigma B0 is exactly singular (sigma is an eigenvalue to working precision; perturb it)");
   return 0;
 }
 

@@ -218,22 +218,3 @@ extern "C" int emu_hess_blocked(cplx* A, int n, int ilo, int ihi, cplx* tau, cpl
   if (Tout) std::memcpy(Tout, T.data(), sizeof(cplx) * T.size());
   return P;
 }
-
-extern "C" int emu_polish(const cplx* A0, const cplx* B0, int n, const cplx* sigma, cplx* x, int max_iters, double tol, double* out4) {
-  std::vector<double> red(256);
-  Cta c = make_cta(red.data());
-  std::vector<cplx> K((size_t)n * n), u(n), v(n), sl(n);
-  std::vector<int> ipiv(n);
-  cta_polish(c, A0, B0, K.data(), n, *sigma, x, u.data(), v.data(), ipiv.data(), sl.data(), max_iters, tol, out4);
-  return 0;
-}
-
-extern "C" int emu_lu_factor_solve(cplx* A, int n, cplx* b) {
-  std::vector<double> red(256);
-  Cta c = make_cta(red.data());
-  std::vector<cplx> sl(n);
-  std::vector<int> ipiv(n);
-  int info = cta_lu_solve(c, A, n, n, nullptr, 0, n, sl.data(), ipiv.data());
-  cta_lu_resolve(c, A, n, n, ipiv.data(), b);
-  return info;
-}

@@ -69,19 +69,21 @@ def eigpair_residuals(M: np.ndarray, w: np.ndarray, V: np.ndarray) -> np.ndarray
     return np.linalg.norm(R, axis=0) / (np.linalg.norm(M) * np.linalg.norm(V, axis=0))
 
 
-def spectrum_parity(M: np.ndarray, ref: np.ndarray, got: np.ndarray, rel_tol=1e-10):
-    """Condition-aware eigenvalue parity (hard part 4).
+def spectrum_parity(M: np.ndarray, ref: np.ndarray, got: np.ndarray, rel_tol=1e-10, floor=10.0, record=None):
+    """Condition-aware eigenvalue parity, PER MODE (hard part 4).
 
     These operators are highly non-normal: two LAPACK runs on the SAME matrix (the reference's
-    lwork=2n ZGEEV vs. an optimal-workspace ZGEEV) already differ by up to ~3e-10 relative on
-    the ill-conditioned continuous-branch modes at Ny=128.  So:
-      (1) every mode for which `rel_tol` is attainable (eps*||Mb||*kappa <= 0.1*rel_tol*|lambda|,
-          computed in ZGEBAL's balanced basis) must agree to rel_tol relative -- this covers the
-          discrete physical modes;
-      (2) every mode must satisfy |d lambda| <= max(rel_tol*|lambda|, C*eps*||Mb||_F*kappa) with
-          C = max(10, 3x the worst LAPACK-vs-LAPACK deviation in the same units): a backward
-          error no worse than 3x the reference library's own reproducibility.
-    Returns a dict of diagnostics; raises AssertionError on violation."""
+    lwork=2n ZGEEV vs. an optimal-workspace ZGEEV on the balanced matrix) already differ by up to
+    ~3e-10 relative on the ill-conditioned continuous-branch modes at Ny=128.  With
+    unit_k = eps*||Mb||_F*kappa_k (first-order sensitivity of mode k in ZGEBAL's balanced basis) and
+    s_k = that mode's own LAPACK-vs-LAPACK scatter:
+      (1) every mode for which `rel_tol` is attainable (unit_k <= 0.1*rel_tol*|lambda_k|) must agree
+          with the oracle to rel_tol relative -- this covers the discrete physical modes;
+      (2) every mode k must satisfy |d lambda_k| <= max(rel_tol*|lambda_k|, C_k*unit_k) with
+          C_k = max(floor, 3*s_k/unit_k): no worse than 3x the reference library's own
+          reproducibility ON THAT MODE, with a floor of `floor` units (a backward error of
+          floor*eps*||Mb||).  One ill-conditioned mode no longer loosens the bound of the others.
+    Returns the diagnostics (also appended to `record` when given); raises AssertionError on violation."""
     import scipy.linalg as sl
     from scipy.linalg import lapack
     eps = 2.0 ** -53
@@ -93,15 +95,48 @@ def spectrum_parity(M: np.ndarray, ref: np.ndarray, got: np.ndarray, rel_tol=1e-
     p_ref, d_ref = match_spectra(w2, ref)          # LAPACK (optimal workspace, balanced input) vs the oracle's as-coded run
     p_got, d_got = match_spectra(w2, got)
     d_got_vs_ref = np.abs(got[p_got] - ref[p_ref])
-    C = max(10.0, 3.0 * float((d_ref / unit).max()))
+    Ck = np.maximum(floor, 3.0 * d_ref / unit)
     mag = np.abs(w2)
     attainable = (unit <= 0.1 * rel_tol * mag) & (mag > 0)
-    out = dict(C=C, n_attainable=int(attainable.sum()),
-               worst_attainable=float((d_got_vs_ref[attainable] / mag[attainable]).max()) if attainable.any() else 0.0,
-               worst_units=float((d_got_vs_ref / unit).max()), lapack_units=float((d_ref / unit).max()))
-    assert out["worst_attainable"] < rel_tol, out
-    bound = np.maximum(rel_tol * mag, C * unit)
-    assert np.all(d_got_vs_ref <= bound), (out, float((d_got_vs_ref / bound).max()))
+    bound = np.maximum(rel_tol * mag, Ck * unit)
+    ratio = d_got_vs_ref / np.maximum(bound, 1e-300)
+    units = d_got_vs_ref / unit
+    out = dict(n=int(w2.size), rel_tol=rel_tol, floor=floor, n_attainable=int(attainable.sum()),
+               worst_attainable_rel=float((d_got_vs_ref[attainable] / mag[attainable]).max()) if attainable.any() else 0.0,
+               worst_units=float(units.max()), median_units=float(np.median(units)),
+               lapack_worst_units=float((d_ref / unit).max()), lapack_median_units=float(np.median(d_ref / unit)),
+               n_modes_on_floor=int(np.sum(Ck <= floor)), worst_bound_ratio=float(ratio.max()),
+               n_rel_tol_met=int(np.sum(d_got_vs_ref <= rel_tol * mag)),
+               worst_rel_all_modes=float((d_got_vs_ref / np.maximum(mag, 1e-300))[mag > 1e-6].max()))
+    if record is not None:
+        record.append(out)
+    assert out["worst_attainable_rel"] < rel_tol, out
+    assert np.all(d_got_vs_ref <= bound), out
+    return out
+
+
+def vector_parity(M, ref_vals, ref_vecs, got_vals, got_vecs, select, tol=1e-8):
+    """Eigenvector parity PER MODE for the modes flagged by `select` (over ref_vals): after scaling every vector to 1 at
+    the oracle vector's entry of maximum modulus, |v_got - v_oracle|_inf <= max(tol, 3 s_k), where s_k is the scatter of
+    a SECOND LAPACK solution (optimal-workspace ZGEEV on the same matrix) about the oracle's for that mode -- the
+    reference library's own reproducibility of that eigenvector.  Returns diagnostics; asserts."""
+    import scipy.linalg as sl
+    w2, v2 = sl.eig(M)
+    p_got, _ = match_spectra(ref_vals, got_vals)
+    p_l2, _ = match_spectra(ref_vals, w2)
+    idx = np.flatnonzero(select)
+    piv = np.argmax(np.abs(ref_vecs[:, idx]), axis=0)
+    cols = np.arange(idx.size)
+
+    def unit(V):
+        return V / V[piv, cols][None, :]
+    vr = unit(ref_vecs[:, idx])
+    dg = np.abs(unit(got_vecs[:, p_got[idx]]) - vr).max(axis=0)
+    dl = np.abs(unit(v2[:, p_l2[idx]]) - vr).max(axis=0)
+    bound = np.maximum(tol, 3.0 * dl)
+    out = dict(n_vectors_compared=int(idx.size), n_within_tol=int(np.sum(dg <= tol)), worst_vector_diff=float(dg.max()),
+               lapack_worst_vector_scatter=float(dl.max()), worst_vector_bound_ratio=float((dg / bound).max()))
+    assert np.all(dg <= bound), out
     return out
 
 

@@ -245,20 +245,3 @@ def test_hess_blocked_matches_zgehrd(n, ilo, ihi):
     assert np.abs(tau[:-1] - rtau).max() < 1e-11
 
 
-def test_polish_shift_invert():
-    """Stage 4: inverse iteration on (A0 - sigma B0) converges to the oracle's TS eigenpair."""
-    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=24)
-    r = so.solve_temporal(p, g["vm"], g["deta"], g["d2eta"], want_vectors=True)
-    phys = np.abs(r["omg"]) < 2.0
-    j = int(np.argmax(np.where(phys, r["omg"].imag, -np.inf)))
-    target = r["omg"][j]
-    n = 5 * p.ny
-    A0c = np.ascontiguousarray(r["A0"].T); B0c = np.ascontiguousarray(r["B0"].T)
-    sigma = np.array([target * (1 + 1e-3)], dtype=np.complex128)
-    x = np.ones(n, dtype=np.complex128)
-    out = np.zeros(4)
-    emu().emu_polish(cptr(A0c), cptr(B0c), n, cptr(sigma), cptr(x), 10, C.c_double(1e-14), cptr(out))
-    lam = complex(out[0], out[1])
-    assert out[3] > 0 and out[2] < 1e-12
-    assert abs(lam - target) < 1e-10 * abs(target)
-    assert np.abs(x - r["evec"][:, j]).max() < 1e-8

@@ -538,14 +538,85 @@ def test_cli_harness_writes_reference_records(tmp_path):
     phys = np.abs(ref["omg"]) < 2.0
     assert (d[phys] / np.maximum(np.abs(ref["omg"][phys]), 1e-3)).max() < 1e-10
     assert eigpair_residuals(ref["M"], back["eval"], back["evec"]).max() < 1e-11
-    # itype 7: the (alpha, beta) sweep of mtemporal.f90 -> eig.1 .. eig.4
+    # itype 7: the (alpha, beta) sweep of mtemporal.f90 -> eig.1 .. eig.4.  The reference reads NO index line for this
+    # itype (stab.f90:46-84 reads `ind` for itype 1-6 only; mtemporal(ind) runs with ind = 0): the same deck goes through
+    # the Python mirror of stab.f90 and through the CLI, and the records must be byte-identical.
     lines = deck.splitlines()
-    sweep = lines[:6] + ["7", "0", "0.1 0.5 0.1", "0.0 0.0 1.0"]      # itype 7, ind, alpha range, beta range
-    r = subprocess.run([cli], input="\n".join(sweep) + "\n", capture_output=True, text=True, cwd=tmp_path)
+    sweep = "\n".join(lines[:6] + ["7", "0.1 0.5 0.1", "0.0 0.0 1.0"]) + "\n"      # itype 7, alpha range, beta range
+    for sub, ievec in (("cli0", "0"), ("cli1", "1")):
+        d = tmp_path / sub
+        d.mkdir()
+        shutil.copy(tmp_path / "profile.0", d / "profile.0")
+        dk = sweep.splitlines()
+        dk[3] = ievec                                                    # deck line 4: ievec
+        dk = "\n".join(dk) + "\n"
+        r = subprocess.run([cli], input=dk, capture_output=True, text=True, cwd=d)
+        assert r.returncode == 0, r.stderr + r.stdout
+        assert sorted(f for f in os.listdir(d) if f.startswith("eig.")) == ["eig.1", "eig.2", "eig.3", "eig.4"]
+        b3 = so.read_eig_file(open(d / "eig.3", "rb").read())
+        assert abs(b3["alpha"] - 0.3) < 1e-15 and b3["ind"] == 0
+        # the header's ievec and the presence of record 5 agree (getevec.f90:90 reads evec iff ievec == 1)
+        assert ("evec" in b3) == (ievec == "1")
+        py = tmp_path / (sub + "_py")
+        py.mkdir()
+        shutil.copy(tmp_path / "profile.0", py / "profile.0")
+        sb.stab(dk, workdir=str(py))
+        for k in (1, 2, 3, 4):
+            assert (d / f"eig.{k}").read_bytes() == (py / f"eig.{k}").read_bytes()
+    if ievec == "1":
+        assert eigpair_residuals(so.solve_temporal(*_point(p, g, 0.3))["M"], b3["eval"], b3["evec"]).max() < 1e-11
+
+
+def _point(p, g, alpha):
+    import copy
+    q = copy.copy(p)
+    q.alpha = complex(alpha)
+    return q, g["vm"], g["deta"], g["d2eta"]
+
+
+def test_cli_itype8_and_ider0(tmp_path):
+    """host/stabgpu_cli: itype 8 (mspatial.f90:20-96, station loop over delta.dat) and ider = 0 (getmean2: first.<ind> /
+    second.<ind>) produce the same records as the Python mirror of stab.f90."""
+    import shutil, subprocess
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stab_b200", "stabgpu_cli")
+    prof = golden_text("ts_profile.0")
+    for sub in ("cli", "py"):
+        d = tmp_path / sub
+        d.mkdir()
+        for ind in (1, 2):
+            (d / f"profile.{ind}").write_text(prof)
+        (d / "delta.dat").write_text("# x_body  delta\n 10.0 0.5\n 20.0 0.45\n")
+    sp = golden_text("ts_spatial_ny32.inp").splitlines()
+    ms = "\n".join(sp[:6] + ["8", "0.06 0.08 0.02", "0.0 0.0 0.0", "1 2 1", "0"]) + "\n"
+    r = subprocess.run([cli], input=ms, capture_output=True, text=True, cwd=tmp_path / "cli")
     assert r.returncode == 0, r.stderr + r.stdout
-    assert sorted(f for f in os.listdir(tmp_path) if f.startswith("eig.")) == ["eig.1", "eig.2", "eig.3", "eig.4"]
-    b3 = so.read_eig_file(open(tmp_path / "eig.3", "rb").read())
-    assert abs(b3["alpha"] - 0.3) < 1e-15 and "evec" not in b3
+    sb.stab(ms, workdir=str(tmp_path / "py"))
+    names = sorted(f for f in os.listdir(tmp_path / "cli") if f.startswith("eig."))
+    assert names == ["eig.1", "eig.2", "eig.3", "eig.4"]
+    for f in names:
+        assert (tmp_path / "cli" / f).read_bytes() == (tmp_path / "py" / f).read_bytes()
+    rec = so.read_eig_file((tmp_path / "cli" / "eig.4").read_bytes())
+    assert rec["ind"] == 2 and rec["x"] == 20.0 and rec["yi"] == 0.9 and abs(rec["omega"] - 0.08) < 1e-15
+    # ider = 0: derivative tables of the same profile next to it
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=24)
+    tab = so.read_profile(prof)
+    import scipy.interpolate as si
+    d1 = np.column_stack([tab[:, 0]] + [si.CubicSpline(tab[:, 0], tab[:, k])(tab[:, 0], 1) for k in range(1, 6)])
+    d2 = np.column_stack([tab[:, 0]] + [si.CubicSpline(tab[:, 0], tab[:, k])(tab[:, 0], 2) for k in range(1, 6)])
+    deck = golden_text("ts_temporal_ny96.inp").splitlines()
+    small = deck[:2] + ["24 1.0 0.0"] + deck[3:]
+    small[4] = "0"                                                   # deck line 5: ider
+    dk = "\n".join(small) + "\n"
+    for sub in ("cli_i0", "py_i0"):
+        d = tmp_path / sub
+        d.mkdir()
+        (d / "profile.0").write_text(prof)
+        np.savetxt(d / "first.0", d1, fmt="%.16e")
+        np.savetxt(d / "second.0", d2, fmt="%.16e")
+    r = subprocess.run([cli], input=dk, capture_output=True, text=True, cwd=tmp_path / "cli_i0")
+    assert r.returncode == 0, r.stderr + r.stdout
+    sb.stab(dk, workdir=str(tmp_path / "py_i0"))
+    assert (tmp_path / "cli_i0" / "evec.dat").read_bytes() == (tmp_path / "py_i0" / "evec.dat").read_bytes()
 
 
 def test_mspatial_stations_delta_dat(tmp_path):

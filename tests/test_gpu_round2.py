@@ -1,0 +1,236 @@
+"""GPU parity tests added in round 2 (run with -m gpu on a B200): parity AT THE BENCHMARKED SIZES (VERDICT r1
+"weak" #1-#3), the batched polish, multi-GPU sharding inside one C-ABI call and the pinned staging ring.
+Everything goes through the C ABI of include/stabgpu.h (ctypes); the oracle is only the checker."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import stab_oracle as so
+from conftest import ROOT
+from helpers import eigpair_residuals, match_spectra, oracle_case, spectrum_parity, to_params, vector_parity
+
+import stab_b200 as sb
+
+pytestmark = pytest.mark.gpu
+
+BENCH_POINTS = 296           # bench.py: points per GPU per step
+PARITY_OUT = os.environ.get("STAB_PARITY_JSON", "")      # profiles/parity_report.py sets this to collect the diagnostics
+
+
+def _bench_alphas():
+    return np.linspace(0.05, 0.45, BENCH_POINTS, endpoint=False)
+
+
+def _record(name, rows):
+    if PARITY_OUT:
+        data = {}
+        if os.path.exists(PARITY_OUT):
+            data = json.load(open(PARITY_OUT))
+        data[name] = rows
+        json.dump(data, open(PARITY_OUT, "w"), indent=1)
+
+
+def test_temporal_ny128_bench_sweep_16_points_with_vectors():
+    """The headline configuration itself (BASELINE configs[1], Ny = 128, n = 640, eigenvectors ON): 16 points spread over
+    the exact alpha sweep bench.py times, each against the oracle -- every mode under the PER-MODE condition-aware
+    bound (1e-10 relative wherever attainable), the least stable discrete mode to 1e-10, eigenvectors of the
+    well-separated physical modes to max(1e-8, 3x LAPACK's own scatter on that vector), every eigenpair's residual."""
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=128)
+    al = _bench_alphas()
+    idx = np.linspace(0, BENCH_POINTS - 1, 16).round().astype(int)
+    omg, ev, info = sb.temporal_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], al + 0j, al * 0j, want_vectors=True)
+    assert np.all(info == 0)
+    rows = []
+    for k in idx:
+        p.alpha = complex(al[k])
+        r = so.solve_temporal(p, g["vm"], g["deta"], g["d2eta"], want_vectors=True)
+        ref = r["omg"]
+        n = ref.size
+        assert np.all(np.diff(omg[k].imag) >= 0)
+        assert np.sum(omg[k] == 0) == np.sum(ref == 0) >= 8
+        d = spectrum_parity(r["M"], ref, omg[k], rel_tol=1e-10)
+        perm, dist = match_spectra(ref, omg[k])
+        phys = np.abs(ref) < 2.0
+        jm = np.argmax(np.where(phys, ref.imag, -np.inf))
+        d["least_stable_rel"] = float(dist[jm] / abs(ref[jm]))
+        assert d["least_stable_rel"] < 1e-10
+        res = eigpair_residuals(r["M"], omg[k], ev[k])
+        d["max_residual"] = float(res.max())
+        assert res.max() < 1e-11
+        kk = np.argmax(np.abs(ev[k]), axis=0)
+        assert np.all(ev[k][kk, np.arange(n)] == 1.0)                     # temporal.f90:867-879
+        sep = np.array([np.min(np.abs(np.delete(ref, j) - ref[j])) for j in range(n)])
+        good = phys & (sep > 1e-3) & (ref != 0)
+        assert good.sum() > 5
+        d.update(vector_parity(r["M"], ref, r["evec"], omg[k], ev[k], good, tol=1e-8))
+        assert d["n_within_tol"] >= 0.9 * d["n_vectors_compared"]        # 1e-8 outright on the bulk of them
+        d["alpha"] = float(al[k]); d["point"] = int(k)
+        rows.append(d)
+    _record("temporal_ny128_bench_sweep", rows)
+
+
+def test_spatial_ny128_with_vectors_parity():
+    """BASELINE configs[3] size with ievec = 1 (companion order 2n = 1280): every mode under the per-mode bound on the
+    companion matrix (1e-10 relative wherever attainable), the TS eigenvalue to 1e-10 and its eigenfunction to 1e-8
+    against the oracle, residuals of the finite modes."""
+    p, g = oracle_case("ts_spatial_ny96.inp", "ts_profile.0", ny=128, ievec=1)
+    alp, ev, info = sb.spatial_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], [p.omega], [p.beta], h5=g["h5"], want_vectors=True)
+    assert info[0] == 0
+    ref = so.solve_spatial(p, g["vm"], g["deta"], g["d2eta"], g["hm"], want_vectors=True)
+    target = complex(2.2804739411367E-001, -6.5163146912049E-003)     # TStest/README.md:10
+    j, jr = so.select_mode(alp[0], target), so.select_mode(ref["alp"], target)
+    assert abs(alp[0][j] - ref["alp"][jr]) < 1e-10 * abs(ref["alp"][jr])
+    n = 5 * p.ny
+    x, xr = ev[0][n:, j], ref["evec"][n:, jr]                          # bottom half = the eigenfunction getevec prints
+    x, xr = x / x[np.argmax(np.abs(x))], xr / xr[np.argmax(np.abs(xr))]
+    assert np.abs(x - xr).max() < 1e-8
+    fin = np.abs(alp[0]) > 1e-8
+    lam = np.where(fin, 1.0 / np.where(fin, alp[0], 1.0), 0.0)
+    lam_ref = ref["lam"]
+    d = spectrum_parity(ref["B0"], lam_ref, lam, rel_tol=1e-10)
+    res = eigpair_residuals(ref["B0"], lam, ev[0])
+    d["ts_mode_rel"] = float(abs(alp[0][j] - ref["alp"][jr]) / abs(ref["alp"][jr]))
+    d["ts_eigenfunction_diff"] = float(np.abs(x - xr).max())
+    d["median_residual_finite"] = float(np.median(res[fin]))
+    assert res[j] < 1e-11 and np.median(res[fin]) < 1e-14
+    _record("spatial_ny128_vectors", [d])
+
+
+def test_polish_batch_temporal_ny128_sweep():
+    """Stage (4), batched: one TS mode per point of a 64-point alpha sweep at Ny = 128 polished from the NEIGHBOURING
+    point's eigenvalue (sweep continuation), no start vector.  Against the full GPU eigensolve on all 64 points, against
+    the oracle eigenpair on 8 of them, and the pencil residual on the oracle's A0, B0."""
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=128)
+    P = to_params(p)
+    al = np.linspace(0.20, 0.36, 64)
+    omg, _, info = sb.temporal_batch(P, g["vm"], g["deta"], g["d2eta"], al + 0j, al * 0j, want_vectors=False)
+    assert np.all(info == 0)
+    ts = np.empty(64, dtype=complex)
+    for k in range(64):                                              # least stable discrete mode with c = omega/alpha in (0.2, 0.6)
+        w = omg[k]
+        c = w.real / al[k]
+        cand = np.where((c > 0.2) & (c < 0.6) & (np.abs(w) < 1.0), w.imag, -np.inf)
+        ts[k] = w[np.argmax(cand)]
+    sigma = np.roll(ts, 1)
+    sigma[0] = ts[0] * (1 + 1e-3)
+    lam, x, resid, iters = sb.polish_batch(1, P, g["vm"], g["deta"], g["d2eta"], al + 0j, al * 0j, sigma, max_iters=12, tol=1e-13)
+    assert np.all(iters > 0) and np.all(iters <= 12)
+    assert np.abs(lam - ts).max() < 1e-10 * np.abs(ts).max()
+    assert resid.max() < 1e-12
+    for k in range(0, 64, 8):
+        p.alpha = complex(al[k])
+        r = so.solve_temporal(p, g["vm"], g["deta"], g["d2eta"], want_vectors=True)
+        j = so.select_mode(r["omg"], ts[k])
+        assert abs(lam[k] - r["omg"][j]) < 1e-10 * abs(r["omg"][j])
+        assert np.abs(x[k] - r["evec"][:, j]).max() < 1e-8            # both scaled as temporal.f90:867-879
+        A0, B0, _ = so.assemble_temporal(p, g["vm"], g["deta"], g["d2eta"])
+        rr = np.linalg.norm(A0 @ x[k] - lam[k] * (B0 @ x[k])) / (np.linalg.norm(A0 @ x[k]) + abs(lam[k]) * np.linalg.norm(B0 @ x[k]))
+        assert rr < 1e-12
+
+
+def test_polish_batch_spatial_vs_oracle():
+    """Spatial polish on the quadratic operator polynomial (C0 + alpha C1 + alpha^2 C2) x = 0: the TS mode at four
+    frequencies, shift 1 % off, against the oracle's companion eigenpair; plus the single-point temporal wrapper."""
+    p, g = oracle_case("ts_spatial_ny96.inp", "ts_profile.0", ny=48)
+    om = np.array([0.06, 0.07, 0.08, 0.09])
+    n = 5 * p.ny
+    refs = []
+    for w in om:
+        p.omega = complex(w)
+        r = so.solve_spatial(p, g["vm"], g["deta"], g["d2eta"], g["hm"], want_vectors=True)
+        a = r["alp"]
+        cand = np.where((a.real > 0.1) & (a.real < 0.4) & (np.abs(a.imag) < 0.05), -a.imag, -np.inf)
+        refs.append((a[np.argmax(cand)], r["evec"][n:, np.argmax(cand)], r))
+    sigma = np.array([q[0] for q in refs]) * (1 + 0.01)
+    lam, x, resid, iters = sb.polish_batch(2, to_params(p), g["vm"], g["deta"], g["d2eta"], om + 0j, om * 0j, sigma, h5=g["h5"],
+                                           max_iters=20, tol=1e-13)
+    assert np.all(iters > 0)
+    for k in range(4):
+        a_ref, v_ref, r = refs[k]
+        assert abs(lam[k] - a_ref) < 1e-10 * abs(a_ref)
+        v = v_ref / v_ref[np.argmax(np.abs(v_ref))]
+        assert np.abs(x[k] - v).max() < 1e-8
+        Pm = r["C0"] + lam[k] * r["C1"] + lam[k] ** 2 * r["C2"]
+        assert np.linalg.norm(Pm @ x[k]) / (np.linalg.norm(r["C0"]) * np.linalg.norm(x[k])) < 1e-12
+    # an exactly singular shift is reported, not iterated on
+    p2, g2 = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=24)
+    ref = so.solve_temporal(p2, g2["vm"], g2["deta"], g2["d2eta"], want_vectors=False)["omg"]
+    jt = so.select_mode(ref, 0.1147 + 0.0024j)
+    l1, x1, r1, it1 = sb.temporal_polish(to_params(p2), g2["vm"], g2["deta"], g2["d2eta"], p2.alpha, p2.beta, ref[jt] * (1 + 0.01), max_iters=30)
+    assert abs(ref[jt] - l1) < 1e-10 and r1 < 1e-12 and it1 > 0
+
+
+def test_pageable_destination_goes_through_the_staging_ring():
+    """The drop-in caller's evec array is pageable (a Fortran allocate): the library stages the vectors through its pinned
+    ring; the result is bit-identical to a page-locked destination and to the ring switched off."""
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=64)
+    P = to_params(p)
+    npts, n = 80, 320
+    al = np.linspace(0.1, 0.4, npts)
+
+    def run(evbuf):
+        omg = np.empty((npts, n), dtype=np.complex128)
+        info = np.zeros(npts, dtype=np.int32)
+        sb.temporal_batch(P, g["vm"], g["deta"], g["d2eta"], al + 0j, al * 0j, want_vectors=True, out=(omg, evbuf, info))
+        assert np.all(info == 0)
+        return omg
+
+    pageable = np.full((npts, n, n), np.nan + 0j)
+    o1 = run(pageable)
+    pinned = np.full((npts, n, n), np.nan + 0j)
+    sb.host_register(pinned)
+    try:
+        o2 = run(pinned)
+    finally:
+        sb.host_unregister(pinned)
+    sb.set_host_staging(0, 0)
+    try:
+        plain = np.full((npts, n, n), np.nan + 0j)
+        o3 = run(plain)
+    finally:
+        sb.set_host_staging(1, 0)
+    assert np.array_equal(o1, o2) and np.array_equal(o1, o3)
+    assert np.array_equal(pageable, pinned) and np.array_equal(pageable, plain)
+    assert not np.isnan(pageable).any()
+
+
+def test_one_batch_call_shards_over_two_gpus_bitwise():
+    """SURVEY 8b / VERDICT r1 missing #2: ONE stabgpu_temporal_batch / stabgpu_spatial_batch / stabgpu_polish_batch call on a
+    multi-GPU box (stabgpu_init_multi) equals the single-device call bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=64)
+    P = to_params(p)
+    al = np.linspace(0.1, 0.4, 101)                                  # odd count: ragged shards
+    sb.init(0)
+    o1, e1, i1 = sb.temporal_batch(P, g["vm"], g["deta"], g["d2eta"], al + 0j, al * 0j, want_vectors=True)
+    l1 = sb.polish_batch(1, P, g["vm"], g["deta"], g["d2eta"], al[:9] + 0j, al[:9] * 0j, o1[:9, 300])
+    ps, gs = oracle_case("ts_spatial_ny32.inp", "ts_profile.0")
+    om = np.linspace(0.05, 0.1, 7)
+    a1, _, j1 = sb.spatial_batch(to_params(ps), gs["vm"], gs["deta"], gs["d2eta"], om + 0j, om * 0j, h5=gs["h5"])
+    try:
+        assert sb.init_multi(2) == 2 and sb.device_count() == 2
+        o2, e2, i2 = sb.temporal_batch(P, g["vm"], g["deta"], g["d2eta"], al + 0j, al * 0j, want_vectors=True)
+        l2 = sb.polish_batch(1, P, g["vm"], g["deta"], g["d2eta"], al[:9] + 0j, al[:9] * 0j, o1[:9, 300])
+        a2, _, j2 = sb.spatial_batch(to_params(ps), gs["vm"], gs["deta"], gs["d2eta"], om + 0j, om * 0j, h5=gs["h5"])
+        # a second call reuses the two cached plans
+        o3, e3, i3 = sb.temporal_batch(P, g["vm"], g["deta"], g["d2eta"], al + 0j, al * 0j, want_vectors=True)
+    finally:
+        sb.init(0)
+    assert np.array_equal(o1, o2) and np.array_equal(e1, e2) and np.array_equal(i1, i2)
+    assert np.array_equal(o1, o3) and np.array_equal(e1, e3)
+    assert np.array_equal(a1, a2) and np.array_equal(j1, j2)
+    assert np.array_equal(l1[0], l2[0]) and np.array_equal(l1[1], l2[1])
+
+
+def test_sweep_enumerators_refuse_degenerate_increments():
+    with pytest.raises(sb.StabGpuError):
+        sb.mtemporal_points(0.1, 0.5, 0.0, 0.0, 0.0, 1.0)
+    with pytest.raises(sb.StabGpuError):
+        sb.mtemporal_points(0.1, 0.5, 0.1, 0.0, 1.0, 0.0)
+    a, b = sb.mtemporal_points(0.1, 0.5, 0.1, 0.0, 0.0, 1.0)
+    assert a.size == 4
