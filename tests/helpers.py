@@ -115,27 +115,38 @@ def spectrum_parity(M: np.ndarray, ref: np.ndarray, got: np.ndarray, rel_tol=1e-
     return out
 
 
-def vector_parity(M, ref_vals, ref_vecs, got_vals, got_vecs, select, tol=1e-8):
-    """Eigenvector parity PER MODE for the modes flagged by `select` (over ref_vals): after scaling every vector to 1 at
-    the oracle vector's entry of maximum modulus, |v_got - v_oracle|_inf <= max(tol, 3 s_k), where s_k is the scatter of
-    a SECOND LAPACK solution (optimal-workspace ZGEEV on the same matrix) about the oracle's for that mode -- the
-    reference library's own reproducibility of that eigenvector.  Returns diagnostics; asserts."""
+def vector_parity(M, ref_vals, ref_vecs, got_vals, got_vecs, select, tol=1e-8, nprobe=3):
+    """Eigenvector parity PER MODE for the modes flagged by `select` (over ref_vals).  Every vector is scaled to 1 at
+    the oracle vector's entry of maximum modulus; then |v_got - v_oracle|_inf <= max(tol, 3 s_k), where s_k is the
+    largest deviation from the oracle's vector among `nprobe` further LAPACK solutions: scipy's optimal-workspace
+    ZGEEV driver on the same matrix, and on the matrix with every entry perturbed by one ulp relative (seeded) --
+    i.e. the reference library's own reproducibility of THAT eigenvector under a backward error of eps |M|, which no
+    method can beat.  `tol` (the north star's 1e-8) must hold wherever it is attainable (3 s_k <= tol).
+    (The first-order bound eps ||M|| sum_j kappa_j / |l_k - l_j| is ~1e3 too pessimistic on these non-normal operators.)
+    Returns diagnostics; asserts."""
     import scipy.linalg as sl
-    w2, v2 = sl.eig(M)
     p_got, _ = match_spectra(ref_vals, got_vals)
-    p_l2, _ = match_spectra(ref_vals, w2)
     idx = np.flatnonzero(select)
     piv = np.argmax(np.abs(ref_vecs[:, idx]), axis=0)
     cols = np.arange(idx.size)
 
     def unit(V):
         return V / V[piv, cols][None, :]
-    vr = unit(ref_vecs[:, idx])
-    dg = np.abs(unit(got_vecs[:, p_got[idx]]) - vr).max(axis=0)
-    dl = np.abs(unit(v2[:, p_l2[idx]]) - vr).max(axis=0)
+    vr0 = unit(ref_vecs[:, idx])
+    dg = np.abs(unit(got_vecs[:, p_got[idx]]) - vr0).max(axis=0)
+    rng = np.random.default_rng(12345)
+    dl = np.zeros(idx.size)
+    for q in range(nprobe):
+        Mq = M if q == 0 else M * (1.0 + 2.0 ** -52 * rng.standard_normal(M.shape))
+        w2, v2 = sl.eig(Mq)
+        p_l2, _ = match_spectra(ref_vals, w2)
+        dl = np.maximum(dl, np.abs(unit(v2[:, p_l2[idx]]) - vr0).max(axis=0))
     bound = np.maximum(tol, 3.0 * dl)
+    att = 3.0 * dl <= tol
     out = dict(n_vectors_compared=int(idx.size), n_within_tol=int(np.sum(dg <= tol)), worst_vector_diff=float(dg.max()),
-               lapack_worst_vector_scatter=float(dl.max()), worst_vector_bound_ratio=float((dg / bound).max()))
+               lapack_worst_vector_scatter=float(dl.max()), worst_vector_bound_ratio=float((dg / bound).max()),
+               n_vectors_tol_attainable=int(att.sum()),
+               worst_vector_diff_where_attainable=float(dg[att].max()) if att.any() else 0.0)
     assert np.all(dg <= bound), out
     return out
 
