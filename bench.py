@@ -35,6 +35,11 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="points in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: a FIXED sweep (BASELINE configs[4], --config c5) sharded over the ranks, gather timed")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"], help="c2: TS alpha sweep Ny=128 (headline); c5: neutral-curve (alpha,Re) points Ny=256, values only")
+    ap.add_argument("--total-points", type=int, default=2048, help="points of the fixed sweep in --scaling strong")
+    ap.add_argument("--no-context", action="store_true", help="skip the library eig context number and the parity sample")
     return ap.parse_args()
 
 
@@ -148,12 +153,14 @@ def run_reference(args):
             break
     ms = 1e3 * float(np.mean(times))
     val = sample / (ms / 1e3)
-    desc = f"{sample} of the sweep's points per step, one worker per core ({used}), 1 BLAS thread each"
+    desc = (f"each step = {sample} points spread over the workload's {args.points}-point sweep (bounded sample), "
+            f"one worker per core ({used}), 1 BLAS thread each; CPU arm is fixed at this box's host cores for every --gpus N")
     line = {
         "impl": "reference", "metric": "full-spectrum eigensolves/sec at Ny=%d" % args.ny, "value": val,
         "unit": "eigensolves/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
-        "config": config_dict(args, sample),
+        "config": config_dict(args, args.points),
+        "sample_points_per_step": sample,
         "cpu_baseline": {"value": val, "unit": "eigensolves/s", "cores": used, "kind": "port", "sample": desc,
                          "lapack": "scipy OpenBLAS zgesv+zgeev('N','%s'), %s workspace" % ("V" if want_vectors else "N", "lwork=2n (as coded)" if as_coded else "optimal")},
         "e2e": {"value": val, "unit": "eigensolves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -229,6 +236,173 @@ def fp64_gemm_peak(torch, dev):
     return best
 
 
+def parity_sample(ny, alpha, omg, ev, k=4):
+    """After the timed loops: `k` points of the timed sweep (rank 0's shard, from the e2e call's output) against the
+    oracle -- the checker, never the thing measured.  max_rel_phys: worst relative distance of a matched eigenvalue over
+    the physical window |omega| < 2 (denominator floored at 1e-3); max_resid: worst ||M v - w v|| / (||M||_F ||v||)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import stab_oracle as so
+    from helpers import match_spectra
+    deck = open(os.path.join(ROOT, "tests", "golden", "ts_temporal_ny96.inp")).read()
+    p = so.read_deck(deck)
+    p.ny = ny
+    p.finish()
+    g = so.prepare(p, open(os.path.join(ROOT, "tests", "golden", "ts_profile.0")).read())
+    idx = np.linspace(0, len(alpha) - 1, k).round().astype(int)
+    worst_rel = worst_res = worst_ts = 0.0
+    for j in idx:
+        p.alpha = complex(alpha[j])
+        r = so.solve_temporal(p, g["vm"], g["deta"], g["d2eta"], want_vectors=False)
+        ref = r["omg"]
+        _, d = match_spectra(ref, omg[j])
+        phys = np.abs(ref) < 2.0
+        worst_rel = max(worst_rel, float((d[phys] / np.maximum(np.abs(ref[phys]), 1e-3)).max()))
+        jm = int(np.argmax(np.where(phys, ref.imag, -np.inf)))       # the least stable discrete mode: what a stability analysis reads
+        worst_ts = max(worst_ts, float(d[jm] / abs(ref[jm])))
+        if ev is not None:
+            V = ev[j].T                                        # library layout (column, row) -> eigenvectors in columns
+            R = r["M"] @ V - V * omg[j][None, :]
+            worst_res = max(worst_res, float((np.linalg.norm(R, axis=0) / (np.linalg.norm(r["M"]) * np.linalg.norm(V, axis=0))).max()))
+    return {"points": [int(j) for j in idx], "max_rel_phys": worst_rel, "max_rel_least_stable_mode": worst_ts,
+            "max_resid": worst_res if ev is not None else None,
+            "note": "max_rel_phys includes the ill-conditioned continuous-branch modes, where two LAPACK runs on the same matrix differ "
+                    "by ~3e-10 (tests/helpers.py::spectrum_parity is the per-mode, condition-aware gate; profiles/r02_parity.json)",
+            "oracle": "oracle/stab_oracle.py (scipy LAPACK zgesv + zgeev, lwork=2n as coded)"}
+
+
+def library_eig_context(torch, dev, ny, alpha, nmat=4):
+    """Context only: the vendor-library route on the same box -- torch.linalg.eig on the device (cuSOLVER
+    Xgeev / MAGMA hybrid, whichever torch dispatches) on `nmat` assembled operators of the sweep, eigenvectors on."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import stab_oracle as so
+        deck = open(os.path.join(ROOT, "tests", "golden", "ts_temporal_ny96.inp")).read()
+        p = so.read_deck(deck)
+        p.ny = ny
+        p.finish()
+        g = so.prepare(p, open(os.path.join(ROOT, "tests", "golden", "ts_profile.0")).read())
+        mats = []
+        for a in alpha[:nmat]:
+            p.alpha = complex(a)
+            A0, B0, _ = so.assemble_temporal(p, g["vm"], g["deta"], g["d2eta"])
+            mats.append(np.linalg.solve(B0, A0))
+        M = torch.as_tensor(np.stack(mats), device=dev)
+        torch.linalg.eig(M[:1])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        torch.linalg.eig(M)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {"library_eig": {"value": nmat / dt, "unit": "eigensolves/s", "matrices": nmat,
+                                "what": "torch.linalg.eig (complex128, eigenvectors) on cuda:0 on the same operators, wall clock; "
+                                        "torch %s dispatches to its CUDA linalg backend (cuSOLVER Xgeev / MAGMA hybrid)" % torch.__version__}}
+    except Exception as ex:                                   # context only: never fail the bench line
+        return {"library_eig": {"unavailable": str(ex)[:200]}}
+
+
+def c5_workload(ny, total):
+    """BASELINE configs[4]: neutral-curve sweep, 100 x 100 grid Re in logspace(2.5, 4) x alpha in
+    linspace(0.02, 0.5), beta = 0, eigenvalues only; `total` of the 10^4 points, spread evenly over the grid in the
+    reference's loop order.  Mean flow: TStest/profile.0 with per-point Re overrides (the boundary-layer similarity
+    profile does not depend on Re)."""
+    import stab_b200 as sb
+    deck = open(os.path.join(ROOT, "tests", "golden", "ts_temporal_ny96.inp")).read()
+    c = sb.read_deck(deck)
+    c.params.ny = ny
+    c.load_profile(os.path.join(ROOT, "tests", "golden", "ts_profile.0"))
+    Re = np.logspace(2.5, 4.0, 100)
+    al = np.linspace(0.02, 0.5, 100)
+    RR, AA = np.meshgrid(Re, al, indexing="ij")
+    idx = np.linspace(0, RR.size - 1, total).round().astype(int)
+    return c, AA.ravel()[idx] + 0j, RR.ravel()[idx].copy()
+
+
+def run_strong(args, torch, sb, dist, world, rank, local, dev):
+    """Strong scaling on BASELINE configs[4]: a FIXED sweep of --total-points (alpha, Re) points at Ny = 256, eigenvalues
+    only, sharded contiguously over the ranks (stabgpu_shard_range); a step = H2D of the shard's sweep values + the hot
+    path + the full eigenvalue gather (NCCL all-gather of the padded shards, then rank 0's D2H of all of them)."""
+    ny = 256 if args.ny == 128 else args.ny
+    n = 5 * ny
+    total = args.total_points
+    case, alpha_all, re_all = c5_workload(ny, total)
+    lo, hi = sb.shard_range(total, rank, world)
+    mine = hi - lo
+    pad = (total + world - 1) // world
+    alpha, Re = alpha_all[lo:hi], re_all[lo:hi]
+    plan = sb.Plan(1, case.params, case.vm, case.deta, case.d2eta, pad, want_vectors=False)
+    if plan.capacity < mine:
+        raise SystemExit(f"bench.py: {mine} points do not fit the device workspace (capacity {plan.capacity})")
+    stream = torch.cuda.ExternalStream(plan.stream(), device=dev)
+    eig_dev = torch.as_tensor(DevArray(plan.eig_dev(), 2 * n * pad), device=dev)
+    gathered = torch.empty(world * eig_dev.numel(), dtype=torch.float64, device=dev)
+    host = torch.empty(gathered.numel(), dtype=torch.float64, pin_memory=True) if rank == 0 else None
+    parts = {"upload": 0.0, "execute": 0.0, "gather": 0.0}
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(acc=None):
+        t0 = time.perf_counter()
+        plan.upload(alpha, alpha * 0, Re_pt=Re)
+        t1 = time.perf_counter()
+        plan.execute()
+        t2 = time.perf_counter()
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered, eig_dev)
+        else:
+            gathered.copy_(eig_dev)
+        if rank == 0:
+            host.copy_(gathered, non_blocking=False)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        if acc is not None:
+            acc["upload"] += t1 - t0; acc["execute"] += t2 - t1; acc["gather"] += t3 - t2
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    with Clocks(local) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(parts)
+        barrier()
+        wall = time.perf_counter() - t0
+    t = torch.tensor([wall, parts["execute"], -parts["execute"], parts["gather"]], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_max, ex_max, ex_min, ga_max = float(t[0]), float(t[1]), -float(t[2]), float(t[3])
+    ms_step = 1e3 * wall_max / args.steps
+    info = plan.info()
+    nfail = torch.tensor([int(np.count_nonzero(info[:mine]))], device=dev)
+    if dist is not None:
+        dist.all_reduce(nfail)
+    stage = plan.stage_times()
+    launches = plan.launch_count() * args.steps
+    if rank == 0:
+        emit({
+            "metric": "full-spectrum eigensolves/sec at Ny=%d" % ny, "value": total / (ms_step * 1e-3), "unit": "eigensolves/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+            "config": {"workload": "neutral-curve sweep (BASELINE configs[4]; SURVEY C5): %d of the 10^4 (alpha, Re) grid points, "
+                                   "Re in logspace(2.5,4) x alpha in linspace(0.02,0.5), beta=0, TStest/profile.0, per-point Re" % total,
+                       "ny": ny, "n": n, "total_points": total, "points_per_gpu_per_step": pad, "eigenvectors": False,
+                       "l2": "per-step working set (points x 16 n^2 B = %.1f GB per GPU) exceeds the 126 MB L2; no explicit flush" % (mine * 16 * n * n / 1e9)},
+            "clocks": clk.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": total / (ms_step * 1e-3), "unit": "eigensolves/s", "h2d_bytes_per_step": int(mine * 40),
+                    "d2h_bytes_per_step": int(16 * n * pad * world),
+                    "call": "plan upload (H2D sweep values) + execute + NCCL all-gather + rank-0 D2H of every eigenvalue, all inside the timed step"},
+            "strong": {"execute_ms_per_step_max_rank": 1e3 * ex_max / args.steps, "execute_ms_per_step_min_rank": 1e3 * ex_min / args.steps,
+                       "gather_ms_per_step_max_rank": 1e3 * ga_max / args.steps, "gather_bytes": int(16 * n * pad * world),
+                       "stages_ms_rank0": stage},
+            "failed_points": int(nfail.item()),
+        })
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 _JSON_OUT = None
 
 
@@ -264,6 +438,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     sb.init(local)
+
+    if args.scaling == "strong":
+        return run_strong(args, torch, sb, dist, world, rank, local, dev)
 
     want_vectors = not args.no_vectors
     P = args.points
@@ -351,6 +528,28 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = P * world * args.steps / float(t.item())
+    # the drop-in caller's arrays are pageable (a Fortran allocate): same call, numpy-allocated destination, served by the
+    # library's pinned staging ring (stabgpu_set_host_staging)
+    omg_p = np.empty((P, n), dtype=np.complex128)
+    ev_p = np.empty((P, n, n), dtype=np.complex128) if want_vectors else None
+    info_p = np.zeros(P, dtype=np.int32)
+    if ev_p is not None:
+        ev_p[:] = 0                                              # touch the pages once (first-touch cost is the caller's, not the call's)
+
+    def e2e_pageable_step():
+        sb.temporal_batch(prm, case.vm, case.deta, case.d2eta, np.array(alpha), np.array(beta), want_vectors=want_vectors, out=(omg_p, ev_p, info_p))
+
+    e2e_pageable_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_pageable_step()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_pageable_val = P * world * args.steps / float(t.item())
+    same_bits = bool(np.array_equal(omg_p, omg_h) and (ev_p is None or np.array_equal(ev_p, ev_h)))
     ny = args.ny
     h2d = 2 * 16 * P + 8 * (ny * 5 * 3 + 3 * ny + 2 * ny * ny)
     d2h = 16 * n * P + (16 * n * n * P if want_vectors else 0) + 4 * P
@@ -391,8 +590,14 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
         pass
+    # ceiling of a one-stage (ZGEHRD / ZLAHR2) reduction: every column needs y = A(k+1:, c+1:) v over the not yet
+    # updated trailing matrix, 16 (ihi-k)(ihi-c) B from HBM per column (296 matrices = 1.9 GB do not fit the 126 MB L2);
+    # even with every other kernel free the stage cannot run faster than those bytes at the measured HBM bandwidth
+    cap_tf = hess_flops / (gemv_bytes / (hbm_peak * 1e9)) / 1e12 if gemv_bytes > 0 else None
     roofline = {"kernel": "Hessenberg stage (k_hb_panel_step + k_hb_gemv + k_gemm_pipe<*>): the graded stage of the north star",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "cap_frac": (cap_tf / peak) if (cap_tf and peak) else None, "target_frac": 0.5,
+                "cap": "HBM ceiling of the per-column GEMV of a one-stage reduction: (40/3) nh^3 flops / (sum 16 (ihi-k)(ihi-c) B / measured HBM GB/s)",
                 "traffic": None, "flops_per_step": hess_flops,
                 "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 burst via torch.matmul (MEASURED_PEAKS.json has no FP64 entry)",
                 "kernel_share_of_step": hess_ms / total_stage}
@@ -418,7 +623,10 @@ def main():
         "config": config_dict(args, P),
         "clocks": clk.summary(),
         "e2e": {"value": e2e_val, "unit": "eigensolves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "call": "stabgpu_temporal_batch, pinned host buffers"},
+                "call": "stabgpu_temporal_batch, pinned host buffers (direct DMA under the eigenvector stage)",
+                "pageable": {"value": e2e_pageable_val, "unit": "eigensolves/s",
+                             "call": "the same call with pageable (numpy) destination arrays: vectors staged through the library's "
+                                     "pinned ring (4 x 64 MB, 4 copy threads)", "bit_identical_to_pinned": same_bits}},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_gemv": roofline_gemv,
@@ -431,6 +639,9 @@ def main():
                               "frac": asm_gbs / hbm_peak if hbm_peak else None},
         "failed_points": n_fail,
     }
+    if not args.no_context:
+        line["parity_sample"] = parity_sample(ny, alpha, omg_h, ev_h)
+        line["context"] = library_eig_context(torch, dev, ny, alpha)
     if not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
         sample = args.cpu_sample or min(P, max(16 * cores, 64))     # ~10-15 s of CPU work on the box's host cores
