@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstabgpu.so")
+LIB_PATH = os.environ.get("STABGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstabgpu.so")
 NDOF = 5
 
 

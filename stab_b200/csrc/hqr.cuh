@@ -20,7 +20,19 @@
 
 namespace stab {
 
-struct Refl { cplx v2; cplx tau; };   // H = I - tau [1;v2][1;v2]^H
+// A bulge step is a complex plane rotation G = [c s; -conj(s) c] (c real, ZLARTG's form) rather than ZLAHQR's
+// 2-element Householder reflector: the same unitary similarity up to a phase, but 12 FMA-class operations per
+// updated pair in FOUR independent chains of depth 3 (the reflector form is 14 operations in two chains of depth
+// 7), and ONE rsqrt on the critical path of a bulge step instead of an rsqrt followed by a reciprocal.  The QR
+// kernel is bound by the latency of dependent FP64 operations (ncu: a third of the stall samples are fixed-latency
+// waits), so chain depth is what this buys: the slab pipeline in isolation runs 10 % faster (scratch/mb/slab_mb.cu).
+struct Rot { cplx s; double c; double pad; };
+
+// Slot of bulge b's reflector inside one time step of the record.  The slab pipeline splits the 16 stages over a lane
+// pair (even lane: stages 0-7, odd lane: 8-15); with the natural order the two lanes of a pair read addresses 256 B apart
+// -- the same shared-memory banks, a 2-way conflict on every reflector load (ncu: 47 % of the slab kernel's shared
+// wavefronts were conflict replays).  Interleaving the halves puts them 32 B apart: different banks, one wavefront.
+SD_HD int rec_slot(int ns, int b) { return ns == 16 ? (((b & 7) << 1) | (b >> 3)) : b; }
 
 struct Grp { int tid, nt; bool warp; };
 SD_DEV void grp_sync(const Grp& g) {
@@ -31,51 +43,57 @@ SD_DEV void grp_sync(const Grp& g) {
 #endif
 }
 
-// 2-element ZLARFG: on return x1 := beta (real), returns {v2, tau}.
-// FP64 divide / sqrt cost ~260 dependent cycles each on sm_100, and this sits on the critical path
-// of every bulge step: one sqrt and two independent reciprocals (no Smith division; the operands
-// are scaled by a power of two only when their squares could leave the safe range).
-SD_DEV Refl larfg2(cplx& x1, cplx x2) {
-  Refl r; r.v2 = mk(0.0, 0.0); r.tau = mk(0.0, 0.0);
-  if (is_zero(x2) && x1.im == 0.0) return r;
-  const double mx = fmax(cabs1(x1), cabs1(x2));
-  double sc = 1.0, isc = 1.0;                               // power-of-two scale and its exact inverse
-  if (mx > 1.0e140 || mx < 1.0e-140) { const int e = ilogb(mx); sc = ldexp(1.0, -e); isc = ldexp(1.0, e); }
-  const cplx a = mk(x1.re * sc, x1.im * sc), b = mk(x2.re * sc, x2.im * sc);
-  const double ss = fma(a.re, a.re, fma(a.im, a.im, fma(b.re, b.re, b.im * b.im)));
+SD_DEV Rot rot_identity() { Rot r; r.s = mk(0.0, 0.0); r.c = 1.0; r.pad = 0.0; return r; }
+SD_DEV bool rot_is_identity(const Rot& r) { return r.s.re == 0.0 && r.s.im == 0.0; }
+
+// G [f; g] = [r; 0]: on return f := r, returns G.  d = 1/sqrt(|f|^2 (|f|^2+|g|^2)), c = |f|^2 d, s = f conj(g) d,
+// r = f (|f|^2+|g|^2) d  (LAPACK 3.10 ZLARTG's unscaled branch).  The operands are scaled by a power of two only when
+// their squares could leave the safe range; |f|^2 underflowing to zero is the f = 0 case (c = 0, a swap).
+SD_DEV Rot lartg2(cplx& f, cplx g) {
+  Rot r = rot_identity();
+  if (is_zero(g)) return r;
+  const double mx = fmax(cabs1(f), cabs1(g));
+  double sc = 1.0;                                          // power-of-two scale
+  if (mx > 1.0e70 || mx < 1.0e-70) { const int e = ilogb(mx); sc = ldexp(1.0, -e); }
+  const cplx a = mk(f.re * sc, f.im * sc), b = mk(g.re * sc, g.im * sc);
+  const double f2 = fma(a.re, a.re, a.im * a.im), g2 = fma(b.re, b.re, b.im * b.im);
+  if (f2 == 0.0) {
 #ifdef STAB_EMU
-  const double inrm = 1.0 / sqrt(ss);
+    const double ig = 1.0 / sqrt(g2);
 #else
-  const double inrm = rsqrt(ss);                          // one MUFU + Newton: no divide, no sqrt on the critical path
+    const double ig = rsqrt(g2);
 #endif
-  const double nrm = ss * inrm;
-  const double sg = (a.re >= 0.0) ? 1.0 : -1.0;           // copysign(1, a.re) with +0 -> +
-  const double beta = -sg * nrm;
-  const double ib = -sg * inrm;                           // 1 / beta
-  r.tau = mk((beta - a.re) * ib, -a.im * ib);
-  const cplx d = mk(a.re - beta, a.im);                 // |d| >= |beta| > 0: no cancellation by the sign choice
+    r.c = 0.0; r.s = mk(b.re * ig, -b.im * ig);
+    f = mk(g2 * ig / sc, 0.0);
+    return r;
+  }
+  const double h2 = f2 + g2;
 #ifdef STAB_EMU
-  const double id = 1.0 / fma(d.re, d.re, d.im * d.im);
+  const double d = 1.0 / sqrt(f2 * h2);
 #else
-  const double id = __drcp_rn(fma(d.re, d.re, d.im * d.im));
+  const double d = rsqrt(f2 * h2);                         // one MUFU + Newton: no divide, no sqrt on the critical path
 #endif
-  r.v2 = mk((b.re * d.re + b.im * d.im) * id, (b.im * d.re - b.re * d.im) * id);
-  x1 = mk(beta * isc, 0.0);
+  r.c = f2 * d;
+  const cplx fd = mk(a.re * d, a.im * d);
+  r.s = mk(fma(fd.re, b.re, fd.im * b.im), fma(fd.im, b.re, -(fd.re * b.im)));   // f conj(g) d
+  const double q = h2 * d;                                  // sqrt(h2) / |f|: scale free
+  f = mk(f.re * q, f.im * q);
   return r;
 }
 
-SD_DEV void apply_left(const Refl& r, cplx& x1, cplx& x2) {    // [x1;x2] := (I - conj(tau) v v^H) [x1;x2]   (14 FMA-class ops)
-  cplx s = x1; fma_acc_conj(s, r.v2, x2);
-  const cplx t = mk(fma(r.tau.re, s.re, r.tau.im * s.im), fma(r.tau.re, s.im, -(r.tau.im * s.re)));   // conj(tau) * s
-  x1.re -= t.re; x1.im -= t.im;
-  fms_acc(x2, t, r.v2);
+SD_DEV void apply_left(const Rot& r, cplx& x1, cplx& x2) {     // [x1;x2] := G [x1;x2]   (12 FMA-class ops, 4 chains of depth 3)
+  const cplx a = x1, b = x2;
+  x1.re = fma(-r.s.im, b.im, fma(r.s.re, b.re, r.c * a.re));
+  x1.im = fma(r.s.im, b.re, fma(r.s.re, b.im, r.c * a.im));
+  x2.re = fma(-r.s.im, a.im, fma(-r.s.re, a.re, r.c * b.re));
+  x2.im = fma(r.s.im, a.re, fma(-r.s.re, a.im, r.c * b.im));
 }
-SD_DEV void apply_right(const Refl& r, cplx& x1, cplx& x2) {   // [x1 x2] := [x1 x2] (I - tau v v^H)
-  cplx s = x1; fma_acc(s, x2, r.v2);
-  const cplx t = mk(fma(s.re, r.tau.re, -(s.im * r.tau.im)), fma(s.re, r.tau.im, s.im * r.tau.re));   // s * tau
-  x1.re -= t.re; x1.im -= t.im;
-  x2.re = fma(-t.re, r.v2.re, x2.re); x2.re = fma(-t.im, r.v2.im, x2.re);                            // x2 -= t * conj(v2)
-  x2.im = fma(-t.im, r.v2.re, x2.im); x2.im = fma(t.re, r.v2.im, x2.im);
+SD_DEV void apply_right(const Rot& r, cplx& x1, cplx& x2) {    // [x1 x2] := [x1 x2] G^H
+  const cplx a = x1, b = x2;
+  x1.re = fma(r.s.im, b.im, fma(r.s.re, b.re, r.c * a.re));
+  x1.im = fma(-r.s.im, b.re, fma(r.s.re, b.im, r.c * a.im));
+  x2.re = fma(r.s.im, a.im, fma(-r.s.re, a.re, r.c * b.re));
+  x2.im = fma(-r.s.im, a.re, fma(-r.s.re, a.im, r.c * b.im));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -85,7 +103,7 @@ SD_DEV void apply_right(const Refl& r, cplx& x1, cplx& x2) {   // [x1 x2] := [x1
 // rows >= rlo.  `rec` (optional) receives the reflectors, (t-ta)*ns + b.
 // ---------------------------------------------------------------------------------------------
 SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int L, int I,
-                  const cplx* shifts, int ns, int ta, int tb, Refl* rec, Refl* cur, long long* prof = nullptr) {
+                  const cplx* shifts, int ns, int ta, int tb, Rot* rec, Rot* cur, long long* prof = nullptr) {
   const int smax = I - 1 - L;
 #ifndef STAB_EMU
   long long pc0 = (prof && g.tid == 0) ? clock64() : 0;
@@ -96,23 +114,23 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
   for (int t = ta; t < tb; ++t) {
     for (int b = g.tid; b < ns; b += g.nt) {
       const int s = t - 2 * b;
-      Refl r; r.v2 = mk(0.0, 0.0); r.tau = mk(0.0, 0.0);
+      Rot r = rot_identity();
       if (s >= 0 && s <= smax) {
         const int kl = L + s - g0;
         if (s == 0) {
           cplx x1 = S[kl + kl * lds] - shifts[b];
           cplx x2 = S[kl + 1 + kl * lds];
-          r = larfg2(x1, x2);
+          r = lartg2(x1, x2);
         } else {
           cplx x1 = S[kl + (kl - 1) * lds];
           cplx x2 = S[kl + 1 + (kl - 1) * lds];
-          r = larfg2(x1, x2);
+          r = lartg2(x1, x2);
           S[kl + (kl - 1) * lds] = x1;
           S[kl + 1 + (kl - 1) * lds] = mk(0.0, 0.0);
         }
       }
       cur[b] = r;
-      if (rec) rec[(t - ta) * ns + b] = r;
+      if (rec) rec[(t - ta) * ns + rec_slot(ns, b)] = r;
     }
     grp_sync(g);
     CHASE_PROF(10);
@@ -127,12 +145,12 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
       const bool mine = g.tid < ncol * ngrp;
 #pragma unroll
       for (int h = 0; h < NPT / NH; ++h) {
-        cplx x1[NH], x2[NH]; Refl rf[NH]; int kk[NH];
+        cplx x1[NH], x2[NH]; Rot rf[NH]; int kk[NH];
 #pragma unroll
         for (int u = 0; u < NH; ++u) {
           const int b = grp + (h * NH + u) * ngrp, s = t - 2 * b;
           kk[u] = -1;
-          rf[u].tau = mk(0.0, 0.0); rf[u].v2 = mk(0.0, 0.0); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
+          rf[u] = rot_identity(); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
           if (mine && b < ns && s >= 0 && s <= smax) {
             const int kl = L + s - g0;
             if (col >= kl) { kk[u] = kl; rf[u] = cur[b]; x1[u] = S[kl + col * lds]; x2[u] = S[kl + 1 + col * lds]; }
@@ -149,12 +167,12 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
       const int row = col;
 #pragma unroll
       for (int h = 0; h < NPT / NH; ++h) {
-        cplx x1[NH], x2[NH]; Refl rf[NH]; int kk[NH];
+        cplx x1[NH], x2[NH]; Rot rf[NH]; int kk[NH];
 #pragma unroll
         for (int u = 0; u < NH; ++u) {
           const int b = grp + (h * NH + u) * ngrp, s = t - 2 * b;
           kk[u] = -1;
-          rf[u].tau = mk(0.0, 0.0); rf[u].v2 = mk(0.0, 0.0); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
+          rf[u] = rot_identity(); x1[u] = mk(0.0, 0.0); x2[u] = mk(0.0, 0.0);
           if (mine && row >= rlo && b < ns && s >= 0 && s <= smax) {
             const int kl = L + s - g0;
             int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
@@ -178,7 +196,7 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
           if (s < 0 || s > smax) continue;
           const int kl = L + s - g0;
           if (col < kl) continue;
-          const Refl r = cur[b];
+          const Rot r = cur[b];
           cplx x1 = S[kl + col * lds], x2 = S[kl + 1 + col * lds];
           apply_left(r, x1, x2);
           S[kl + col * lds] = x1; S[kl + 1 + col * lds] = x2;
@@ -195,7 +213,7 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
           const int kl = L + s - g0;
           int rmax = kl + 2; if (rmax > I - g0) rmax = I - g0;
           if (row > rmax) continue;
-          const Refl r = cur[b];
+          const Rot r = cur[b];
           cplx x1 = S[row + kl * lds], x2 = S[row + (kl + 1) * lds];
           apply_right(r, x1, x2);
           S[row + kl * lds] = x1; S[row + (kl + 1) * lds] = x2;
@@ -223,45 +241,45 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
 // S is the wsz x wsz window with global origin g0 (rows above the active block are never inside:
 // g0 >= L).  cur holds 2*ns reflectors.  rec receives reflector (t, b) at (t-ta)*ns + b.
 // ---------------------------------------------------------------------------------------------
-SD_DEV Refl zero_refl() { Refl r; r.v2 = mk(0.0, 0.0); r.tau = mk(0.0, 0.0); return r; }
+SD_DEV Rot zero_refl() { Rot r = rot_identity(); return r; }
 
 template <int NSC>
 SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, int I,
-                        const cplx* shifts, int ns_rt, int ta, int tb, Refl* rec, Refl* cur) {
+                        const cplx* shifts, int ns_rt, int ta, int tb, Rot* rec, Rot* cur) {
   const int ns = NSC ? NSC : ns_rt;                          // compile-time shift count when known (index arithmetic by shifts)
   const int smax = I - 1 - L;
   const int kb0 = L - g0;                                   // local position of a bulge at s = 0
   const int ilast = I - g0;                                 // last local row / column of the active block
   // prologue: reflectors of step ta (as `chase` generates them at the start of a step)
   {
-    Refl* cb = cur + (ta & 1) * ns;
+    Rot* cb = cur + (ta & 1) * ns;
     for (int b = g.tid; b < ns; b += g.nt) {
       const int s = ta - 2 * b;
-      Refl r = zero_refl();
+      Rot r = zero_refl();
       if (s >= 0 && s <= smax) {
         const int kl = kb0 + s;
         if (s == 0) {
           cplx x1 = S[kl + kl * lds] - shifts[b];
           cplx x2 = S[kl + 1 + kl * lds];
-          r = larfg2(x1, x2);
+          r = lartg2(x1, x2);
         } else {
           cplx x1 = S[kl + (kl - 1) * lds];
           cplx x2 = S[kl + 1 + (kl - 1) * lds];
-          r = larfg2(x1, x2);
+          r = lartg2(x1, x2);
           S[kl + (kl - 1) * lds] = x1;
           S[kl + 1 + (kl - 1) * lds] = mk(0.0, 0.0);
         }
       }
       cb[b] = r;
-      rec[b] = r;
+      rec[rec_slot(ns, b)] = r;
     }
   }
   grp_sync(g);
   const int nbt = (g.nt >= 64) ? 32 : 0;                    // threads reserved for the bulge jobs (first warp)
   const int ntile = ns * (ns - 1) / 2;
   for (int t = ta; t < tb; ++t) {
-    const Refl* cb = cur + (t & 1) * ns;
-    Refl* nb = cur + ((t + 1) & 1) * ns;
+    const Rot* cb = cur + (t & 1) * ns;
+    Rot* nb = cur + ((t + 1) & 1) * ns;
     const bool more = (t + 1 < tb);
     // active bulges at time t: blo..bhi (s = t - 2b in [0, smax])
     int bhi = t >> 1; if (bhi > ns - 1) bhi = ns - 1;
@@ -270,7 +288,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
     if (g.tid < (nbt ? ns : g.nt)) {
       for (int b = g.tid; b < ns; b += (nbt ? ns : g.nt)) {
         const int s = t - 2 * b;
-        Refl rn = zero_refl();
+        Rot rn = zero_refl();
         if (s >= 0 && s <= smax) {
           const int k = kb0 + s;
           const bool has3 = (k + 2 <= ilast);
@@ -278,12 +296,12 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
           cplx a01 = S[k + (k + 1) * lds], a11 = S[k + 1 + (k + 1) * lds];
           cplx a20 = mk(0.0, 0.0), a21 = mk(0.0, 0.0);
           if (has3) { a20 = S[k + 2 + k * lds]; a21 = S[k + 2 + (k + 1) * lds]; }
-          const Refl r = cb[b];
+          const Rot r = cb[b];
           apply_left(r, a00, a10); apply_left(r, a01, a11);
           apply_right(r, a00, a01); apply_right(r, a10, a11);
           if (has3) apply_right(r, a20, a21);
           if (more && s + 1 <= smax) {                       // reflector of step t+1 from column k, rows k+1, k+2
-            rn = larfg2(a10, a20);
+            rn = lartg2(a10, a20);
             a20 = mk(0.0, 0.0);
           }
           S[k + k * lds] = a00; S[k + 1 + k * lds] = a10;
@@ -292,10 +310,10 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
         } else if (s == -1 && more && smax >= 0) {           // bulge b enters at step t+1
           cplx x1 = S[kb0 + kb0 * lds] - shifts[b];
           cplx x2 = S[kb0 + 1 + kb0 * lds];
-          rn = larfg2(x1, x2);
+          rn = lartg2(x1, x2);
         }
         nb[b] = rn;
-        if (more) rec[(t + 1 - ta) * ns + b] = rn;
+        if (more) rec[(t + 1 - ta) * ns + rec_slot(ns, b)] = rn;
       }
     }
     // ---- tile and line jobs -----------------------------------------------------------------
@@ -317,7 +335,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
         const int kr = kb0 + t - 2 * b, kc = kb0 + t - 2 * bp;
         cplx* q0 = S + kr + kc * lds;
         cplx a00 = q0[0], a10 = q0[1], a01 = q0[lds], a11 = q0[lds + 1];
-        const Refl rl = cb[b], rr = cb[bp];
+        const Rot rl = cb[b], rr = cb[bp];
         apply_left(rl, a00, a10); apply_left(rl, a01, a11);
         apply_right(rr, a00, a01); apply_right(rr, a10, a11);
         q0[0] = a00; q0[1] = a10; q0[lds] = a01; q0[lds + 1] = a11;
@@ -410,7 +428,7 @@ struct SmallCtl { int L; int pad; cplx shift; };
 // All eigenvalues of the m x m upper Hessenberg matrix S (shared memory), single-shift QR.
 // Returns the number of eigenvalues that failed to converge (0 = success); converged ones are in
 // wout[...], for failures wout holds the current diagonal.
-SD_DEV int smem_hqr(const Grp& g, cplx* S, int lds, int m, cplx* wout, SmallCtl* ctl, Refl* cur) {
+SD_DEV int smem_hqr(const Grp& g, cplx* S, int lds, int m, cplx* wout, SmallCtl* ctl, Rot* cur, Rot* rec) {
   const double smlnum = SD_SAFMIN * ((double)m / SD_ULP);
   int I = m - 1;
   int its = 0;
@@ -449,7 +467,9 @@ SD_DEV int smem_hqr(const Grp& g, cplx* S, int lds, int m, cplx* wout, SmallCtl*
       return I + 1;
     }
     its += 1;
-    chase(g, S, lds, 0, L, I, L, I, &ctl->shift, 1, 0, I - L, nullptr, cur);
+    // one bulge through the active block [L, I] with ONE barrier per step (chase_tiles on the block as its own window;
+    // rows above and columns right of the block are not needed for eigenvalues); `rec` is scratch here
+    chase_tiles<0>(g, S + L + (size_t)L * lds, lds, L, I - L + 1, L, I, &ctl->shift, 1, 0, I - L, rec, cur);
   }
   return 0;
 }
@@ -457,9 +477,9 @@ SD_DEV int smem_hqr(const Grp& g, cplx* S, int lds, int m, cplx* wout, SmallCtl*
 struct HqrSmem {
   cplx* win;     // W * ldw
   int ldw, W;
-  Refl* rec;     // steps_max * ns_max
+  Rot* rec;     // steps_max * ns_max
   int steps_max, ns_max;
-  Refl* cur;     // 2 * ns_max (double-buffered by chase_tiles)
+  Rot* cur;     // 2 * ns_max (double-buffered by chase_tiles)
   cplx* shifts;  // ns_max
   cplx* sm;      // ns_max * (ns_max + 1)   trailing block for the shift computation
   SmallCtl* ctl;
@@ -492,7 +512,7 @@ struct HqrSmem {
 constexpr int SLAB_PF = 4;   // input prefetch distance (time steps)
 
 template <int NSB, bool RIGHT, bool STEADY>
-SD_NOINLINE void slab_line(cplx* base, size_t stride, int L, int smax, int ta, int tb, const Refl* rec) {
+SD_NOINLINE void slab_line(cplx* base, size_t stride, int L, int smax, int ta, int tb, const Rot* rec) {
   cplx st[NSB], pipe[NSB];
 #pragma unroll
   for (int b = 0; b < NSB; ++b) {                         // prologue: elements in flight at time ta
@@ -517,7 +537,7 @@ SD_NOINLINE void slab_line(cplx* base, size_t stride, int L, int smax, int ta, i
           const int tn = t + SLAB_PF;
           if (tn < tb && tn <= smax) inq[u] = base[(size_t)(L + tn + 1) * stride];
         }
-        const Refl* rt = rec + (size_t)(t - ta) * NSB;
+        const Rot* rt = rec + (size_t)(t - ta) * NSB;
 #pragma unroll
         for (int bb = 0; bb < NSB; ++bb) {
           const int b = NSB - 1 - bb;                     // descending: consume pipe[b] before stage b-1 refills it
@@ -525,8 +545,8 @@ SD_NOINLINE void slab_line(cplx* base, size_t stride, int L, int smax, int ta, i
           if (STEADY || (s >= 0 && s <= smax)) {
             cplx x1 = st[b];
             cplx x2 = (b == 0) ? xin : pipe[b];
-            const Refl r = rt[b];
-            if (RIGHT) apply_right(r, x1, x2); else apply_left(r, x1, x2);   // tau = 0 is an exact identity
+            const Rot r = rt[rec_slot(NSB, b)];
+            if (RIGHT) apply_right(r, x1, x2); else apply_left(r, x1, x2);   // c = 1, s = 0 is an exact identity
             if (b == NSB - 1) base[(size_t)(L + s) * stride] = x1; else pipe[b + 1 < NSB ? b + 1 : b] = x1;
             st[b] = x2;
           } else if (s == -1) {
@@ -557,28 +577,32 @@ SD_NOINLINE void slab_line(cplx* base, size_t stride, int L, int smax, int ta, i
 // vacated, and the kept value stays in B[bl] -- so at the next step B holds the resident elements
 // and A the inputs.  One step:
 template <int NL, bool RIGHT, bool STEADY>
-SD_DEV void slab_pair_step(cplx (&A)[NL], cplx (&B)[NL], cplx& outp, const Refl* __restrict__ rt, int part, int b0, int t,
-                           int L, int smax, cplx* base, size_t stride) {
+SD_DEV void slab_pair_step(cplx (&A)[NL], cplx (&B)[NL], cplx& outp, const Rot* __restrict__ rt, int part, int b0, int t,
+                           int L, int smax, cplx* base, size_t stride, bool act) {
 #pragma unroll
   for (int bb = 0; bb < NL; ++bb) {
     const int bl = NL - 1 - bb, b = b0 + bl, s = t - 2 * b;    // descending: stage bl+1 has vacated A[bl+1]
     if (STEADY || (s >= 0 && s <= smax)) {
       cplx x1 = A[bl];
       cplx x2 = B[bl];
-      const Refl r = rt[bl];
-      if (RIGHT) apply_right(r, x1, x2); else apply_left(r, x1, x2);   // tau = 0 is an exact identity
-      if (bl == NL - 1) { if (part == 1) base[(size_t)(L + s) * stride] = x1; else outp = x1; }
+      const Rot r = rt[2 * bl];                                  // rec_slot: stage b0 + bl lives at 2 bl + part
+      if (RIGHT) apply_right(r, x1, x2); else apply_left(r, x1, x2);   // c = 1, s = 0 is an exact identity
+      if (bl == NL - 1) { if (part == 1) { if (act) base[(size_t)(L + s) * stride] = x1; } else outp = x1; }
       else A[bl + 1 < NL ? bl + 1 : bl] = x1;
       B[bl] = x2;
     } else if (s == smax + 1) {                                 // flush the resident element
-      if (bl == NL - 1) { if (part == 1) base[(size_t)(L + s) * stride] = A[bl]; else outp = A[bl]; }
+      if (bl == NL - 1) { if (part == 1) { if (act) base[(size_t)(L + s) * stride] = A[bl]; } else outp = A[bl]; }
       else A[bl + 1 < NL ? bl + 1 : bl] = A[bl];
     }                                                           // s == -1: the arrived element (B[bl]) becomes resident by the role swap
   }
 }
 
 template <int NSB, bool RIGHT, bool STEADY>
-SD_NOINLINE void slab_line_pair(cplx* base, size_t stride, int L, int smax, int ta, int tb, const Refl* rec, unsigned mask, int part) {
+// Every lane of the warp runs the schedule (the shuffles take the constant full mask: a computed mask costs a
+// MATCH / REDUX / VOTE / divergence-check sequence per time step); a lane pair without a line (`act` false, only in
+// the last unit of a slab) computes on zeros and never touches memory.
+SD_NOINLINE void slab_line_pair(cplx* base, size_t stride, int L, int smax, int ta, int tb, const Rot* rec, bool act, int part) {
+  constexpr unsigned mask = 0xffffffffu;
   constexpr int NL = NSB / 2;
   static_assert(SLAB_PF % 2 == 0, "the role alternation needs an even unroll");
   const int b0 = part * NL;
@@ -587,14 +611,15 @@ SD_NOINLINE void slab_line_pair(cplx* base, size_t stride, int L, int smax, int 
   for (int bl = 0; bl < NL; ++bl) {                       // prologue: elements in flight at time ta
     const int b = b0 + bl, s = ta - 2 * b;
     P[bl] = mk(0.0, 0.0); Q[bl] = mk(0.0, 0.0);
-    if (STEADY || (s >= 0 && s <= smax + 1)) P[bl] = base[(size_t)(L + s) * stride];
-    if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) Q[bl] = base[(size_t)(L + s + 1) * stride];
+    if (act && (STEADY || (s >= 0 && s <= smax + 1))) P[bl] = base[(size_t)(L + s) * stride];
+    if (act && b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) Q[bl] = base[(size_t)(L + s + 1) * stride];
   }
+  const bool feed = act && part == 0;
   cplx inq[SLAB_PF];
 #pragma unroll
   for (int u = 0; u < SLAB_PF; ++u) {
     const int t = ta + u;
-    inq[u] = (part == 0 && t < tb && t <= smax) ? base[(size_t)(L + t + 1) * stride] : mk(0.0, 0.0);
+    inq[u] = (feed && t < tb && t <= smax) ? base[(size_t)(L + t + 1) * stride] : mk(0.0, 0.0);
   }
   cplx outp = mk(0.0, 0.0);                               // emission of this lane's last stage at the previous step
   for (int t0 = ta; t0 < tb; t0 += SLAB_PF) {
@@ -605,16 +630,16 @@ SD_NOINLINE void slab_line_pair(cplx* base, size_t stride, int L, int smax, int 
         const cplx xin = inq[u];
         {
           const int tn = t + SLAB_PF;
-          if (part == 0 && tn < tb && tn <= smax) inq[u] = base[(size_t)(L + tn + 1) * stride];
+          if (feed && tn < tb && tn <= smax) inq[u] = base[(size_t)(L + tn + 1) * stride];
         }
         const cplx got = mk(__shfl_xor_sync(mask, outp.re, 1), __shfl_xor_sync(mask, outp.im, 1));
-        const Refl* rt = rec + (size_t)(t - ta) * NSB + b0;
+        const Rot* rt = rec + (size_t)(t - ta) * NSB + part;
         if ((u & 1) == 0) {
           if (part == 0) Q[0] = xin; else if (t > ta) Q[0] = got;
-          slab_pair_step<NL, RIGHT, STEADY>(P, Q, outp, rt, part, b0, t, L, smax, base, stride);
+          slab_pair_step<NL, RIGHT, STEADY>(P, Q, outp, rt, part, b0, t, L, smax, base, stride, act);
         } else {
           if (part == 0) P[0] = xin; else P[0] = got;
-          slab_pair_step<NL, RIGHT, STEADY>(Q, P, outp, rt, part, b0, t, L, smax, base, stride);
+          slab_pair_step<NL, RIGHT, STEADY>(Q, P, outp, rt, part, b0, t, L, smax, base, stride, act);
         }
       }
     }
@@ -625,23 +650,23 @@ SD_NOINLINE void slab_line_pair(cplx* base, size_t stride, int L, int smax, int 
 #pragma unroll
     for (int bl = 0; bl < NL; ++bl) {                     // epilogue: park the elements still in flight
       const int b = b0 + bl, s = tb - 2 * b;
-      if (STEADY || (s >= 0 && s <= smax + 1)) base[(size_t)(L + s) * stride] = P[bl];
-      if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) base[(size_t)(L + s + 1) * stride] = Q[bl];
+      if (act && (STEADY || (s >= 0 && s <= smax + 1))) base[(size_t)(L + s) * stride] = P[bl];
+      if (act && b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) base[(size_t)(L + s + 1) * stride] = Q[bl];
     }
   } else {
     if (part == 1) P[0] = got;
 #pragma unroll
     for (int bl = 0; bl < NL; ++bl) {
       const int b = b0 + bl, s = tb - 2 * b;
-      if (STEADY || (s >= 0 && s <= smax + 1)) base[(size_t)(L + s) * stride] = Q[bl];
-      if (b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) base[(size_t)(L + s + 1) * stride] = P[bl];
+      if (act && (STEADY || (s >= 0 && s <= smax + 1))) base[(size_t)(L + s) * stride] = Q[bl];
+      if (act && b >= 1 && (STEADY || (s + 1 >= 0 && s + 1 <= smax + 1))) base[(size_t)(L + s + 1) * stride] = P[bl];
     }
   }
 }
 #endif
 
 template <int NSB>
-SD_DEV void slabs_stream(const Cta& c, cplx* H, int ldh, int L, int I, int g0, int g1, int ta, int tb, const Refl* rec) {
+SD_DEV void slabs_stream(const Cta& c, cplx* H, int ldh, int L, int I, int g0, int g1, int ta, int tb, const Rot* rec) {
   const int smax = I - 1 - L;
   const bool steady = (ta >= 2 * (NSB - 1)) && (tb - 1 <= smax);
 #ifndef STAB_EMU
@@ -651,25 +676,43 @@ SD_DEV void slabs_stream(const Cta& c, cplx* H, int ldh, int L, int I, int g0, i
     const int part = c.tid & 1, lp = c.lane >> 1;
     const int nleft = I - g1, nright = g0 - L;              // left slab columns (g1, I], right slab rows [L, g0)
     const int UL = (nleft + 15) >> 4, UR = (nright + 15) >> 4;
+    const int p0 = L + (ta > 2 * (NSB - 1) ? ta - 2 * (NSB - 1) : 0);     // first position this pass touches
+    int p1 = L + tb + 1; if (p1 > I) p1 = I;                             // last one
     for (int u = c.wid; u < UL + UR; u += c.nw) {
+#ifndef STAB_QR_NO_L2PF
+      {
+        // The 2 x NSB elements a line has in flight are loaded at the start of its unit and nothing hides that latency
+        // (ncu: 20 % of the slab samples wait on global loads): pull the NEXT unit of this warp into L2 now, so that its
+        // prologue and its streamed inputs are L2 hits by the time they are issued.  No registers, no shared memory.
+        const int u2 = u + c.nw;
+        if (u2 < UL) {                                                   // 16 columns x (p1 - p0 + 1) rows, contiguous per column
+          const int li2 = (u2 << 4) + (c.lane >> 1);
+          if (li2 < nleft) {
+            const char* q = reinterpret_cast<const char*>(H + (size_t)(g1 + 1 + li2) * ldh + p0);
+            const int nb = (p1 - p0 + 1) * 16;
+            for (int o = (c.lane & 1) * 128; o < nb; o += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
+          }
+        } else if (u2 < UL + UR) {                                       // 16 rows (256 B) of every touched column
+          const int r0 = L + ((u2 - UL) << 4);
+          for (int col = p0 + (c.lane >> 1); col <= p1; col += 16) {
+            const char* q = reinterpret_cast<const char*>(H + r0 + (size_t)col * ldh) + (c.lane & 1) * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+          }
+        }
+      }
+#endif
       if (u < UL) {
         const int li = (u << 4) + lp;
         const bool act = li < nleft;
-        const unsigned mask = __ballot_sync(0xffffffffu, act);
-        if (act) {
-          cplx* line = H + (size_t)(g1 + 1 + li) * ldh;
-          if (steady) slab_line_pair<NSB, false, true>(line, 1, L, smax, ta, tb, rec, mask, part);
-          else slab_line_pair<NSB, false, false>(line, 1, L, smax, ta, tb, rec, mask, part);
-        }
+        cplx* line = H + (size_t)(g1 + 1 + (act ? li : 0)) * ldh;
+        if (steady) slab_line_pair<NSB, false, true>(line, 1, L, smax, ta, tb, rec, act, part);
+        else slab_line_pair<NSB, false, false>(line, 1, L, smax, ta, tb, rec, act, part);
       } else {
         const int li = ((u - UL) << 4) + lp;
         const bool act = li < nright;
-        const unsigned mask = __ballot_sync(0xffffffffu, act);
-        if (act) {
-          cplx* line = H + (L + li);
-          if (steady) slab_line_pair<NSB, true, true>(line, (size_t)ldh, L, smax, ta, tb, rec, mask, part);
-          else slab_line_pair<NSB, true, false>(line, (size_t)ldh, L, smax, ta, tb, rec, mask, part);
-        }
+        cplx* line = H + (L + (act ? li : 0));
+        if (steady) slab_line_pair<NSB, true, true>(line, (size_t)ldh, L, smax, ta, tb, rec, act, part);
+        else slab_line_pair<NSB, true, false>(line, (size_t)ldh, L, smax, ta, tb, rec, act, part);
       }
     }
   }
@@ -743,8 +786,8 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
         cplx x = hc[k];
         for (int t = t0; t <= t1; ++t, ++k) {
           cplx y = hc[k + 1];
-          const Refl r = sh.rec[(t - ta) * ns + b];
-          if (!is_zero(r.tau)) apply_left(r, x, y);
+          const Rot r = sh.rec[(t - ta) * ns + rec_slot(ns, b)];
+          if (!rot_is_identity(r)) apply_left(r, x, y);
           hc[k] = x;
           x = y;
         }
@@ -764,8 +807,8 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
         cplx x = hr[(size_t)k * ldh];
         for (int t = t0; t <= t1; ++t, ++k) {
           cplx y = hr[(size_t)(k + 1) * ldh];
-          const Refl r = sh.rec[(t - ta) * ns + b];
-          if (!is_zero(r.tau)) apply_right(r, x, y);
+          const Rot r = sh.rec[(t - ta) * ns + rec_slot(ns, b)];
+          if (!rot_is_identity(r)) apply_right(r, x, y);
           hr[(size_t)k * ldh] = x;
           x = y;
         }
@@ -822,13 +865,13 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
       if (m <= 40) {                           // small: one warp with warp-level barriers beats CTA barriers
         if (c.wid == 0) {
           Grp gw; gw.tid = c.lane; gw.nt = c.ws; gw.warp = true;
-          bad = smem_hqr(gw, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur);
+          bad = smem_hqr(gw, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur, sh.rec);
           if (c.lane == 0) sh.ctl->pad = bad;
         }
         cta_sync();
         bad = sh.ctl->pad;
       } else {
-        bad = smem_hqr(g, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur);
+        bad = smem_hqr(g, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur, sh.rec);
       }
       if (bad) info += bad;
       I = L - 1; stagn = 0;
@@ -859,7 +902,7 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
       cta_sync();
       if (c.wid == 0) {                        // a 16x16 problem: one warp, warp-level barriers
         Grp gw; gw.tid = c.lane; gw.nt = c.ws; gw.warp = true;
-        smem_hqr(gw, sh.sm, lds, ns, sh.shifts, sh.ctl, sh.cur);
+        smem_hqr(gw, sh.sm, lds, ns, sh.shifts, sh.ctl, sh.cur, sh.rec);
       }
       cta_sync();
     }

@@ -6,12 +6,11 @@
 #include "assemble.cuh"
 #include "balance.cuh"
 #include "hessenberg.cuh"
-#include "hqr.cuh"
 #include "gemm_pipe.cuh"
 #include "evec.cuh"
 #include "lu.cuh"
 #include "hess_blocked.cuh"
-#include "invit.cuh"
+#include "launch.h"
 
 namespace stab {
 
@@ -445,49 +444,7 @@ __global__ void k_prep_qr(const cplx* A, size_t astride, cplx* Hq, size_t hstrid
     }
 }
 
-// ---- stage 4: shifted QR ------------------------------------------------------------------------
-struct HqrLaunch { int W, ns_max, steps_max; };
-SD_HD size_t hqr_smem_bytes(const HqrLaunch& q) {
-  size_t b = 160 * sizeof(double);
-  b += (size_t)q.W * (q.W + 1) * sizeof(cplx);
-  b += (size_t)q.steps_max * q.ns_max * sizeof(Refl);
-  b += (size_t)2 * q.ns_max * sizeof(Refl);
-  b += (size_t)q.ns_max * sizeof(cplx);
-  b += (size_t)q.ns_max * (q.ns_max + 1) * sizeof(cplx);
-  b += sizeof(SmallCtl);
-  return b;
-}
-
-__global__ void __launch_bounds__(256, 2) k_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q, long long* prof, const double* hnorm) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned char* sp = smem_raw;
-  double* red = reinterpret_cast<double*>(sp); sp += 160 * sizeof(double);
-  HqrSmem sh;
-  sh.W = q.W; sh.ldw = q.W + 1; sh.ns_max = q.ns_max; sh.steps_max = q.steps_max;
-  sh.win = reinterpret_cast<cplx*>(sp); sp += (size_t)q.W * (q.W + 1) * sizeof(cplx);
-  sh.rec = reinterpret_cast<Refl*>(sp); sp += (size_t)q.steps_max * q.ns_max * sizeof(Refl);
-  sh.cur = reinterpret_cast<Refl*>(sp); sp += (size_t)2 * q.ns_max * sizeof(Refl);
-  sh.shifts = reinterpret_cast<cplx*>(sp); sp += (size_t)q.ns_max * sizeof(cplx);
-  sh.sm = reinterpret_cast<cplx*>(sp); sp += (size_t)q.ns_max * (q.ns_max + 1) * sizeof(cplx);
-  sh.ctl = reinterpret_cast<SmallCtl*>(sp);
-  Cta c = make_cta(red);
-  const int p = blockIdx.x;
-  __shared__ long long sprof[16];
-  sh.prof = (prof && p == 0) ? sprof : nullptr;
-  if (sh.prof && threadIdx.x < 16) sprof[threadIdx.x] = 0;
-  __syncthreads();
-  // A matrix with a NaN or an infinity (bad sweep value, overflowed operator) never deflates: report it as ZHSEQR's
-  // "failed to converge" at once (info = n) instead of iterating to the limit; the other points of the batch go on.
-  const double hn = hnorm[p];
-  if (!(hn == hn) || hn > 1.0e300) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) w[(size_t)p * n + i] = mk(hn - hn, hn - hn);   // NaN
-    if (threadIdx.x == 0) info[p] = n;
-    return;
-  }
-  int r = cta_hqr(c, sh, Hq + (size_t)p * hstride, n, n, ilohi[2 * p], ilohi[2 * p + 1], w + (size_t)p * n);
-  if (threadIdx.x == 0) info[p] = r;
-  if (sh.prof && threadIdx.x < 16) prof[threadIdx.x] = sprof[threadIdx.x];
-}
+// ---- stage 4: shifted QR: qr.cu (its own translation unit, launch.h) -------------------------------
 
 // ---- stage 5: sort (stable, ascending imaginary part) --------------------------------------------
 // mode 1 (temporal): key = Im(w).  mode 2 (spatial): alpha = 1/lambda (0 if lambda == 0), key = Im(alpha)

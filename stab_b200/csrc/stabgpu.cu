@@ -373,35 +373,6 @@ int launch_bt_gemm(stabgpu_plan* pl, const HessBatch& hb, int nmat, int panel, i
   return 0;
 }
 
-template <int NS>
-int launch_invit(stabgpu_plan* pl, int rounds, int m0, int cnt) {
-  const int N = pl->N;
-  const size_t st = (size_t)N * N;
-  const size_t sm = 2 * (size_t)INVIT_CB * N * sizeof(cplx) + (size_t)INVIT_WARPS * N;
-  CU(cudaFuncSetAttribute(k_invit<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  dim3 grid((N + INVIT_WARPS * rounds - 1) / (INVIT_WARPS * rounds), cnt);
-  k_invit<NS><<<grid, INVIT_WARPS * 32, sm, pl->stream>>>(pl->A.p + (size_t)m0 * st, st, N, pl->lam.p + (size_t)m0 * N, pl->kr.p + (size_t)m0 * N,
-                                                          pl->hnorm.p + m0, pl->V.p + (size_t)m0 * st, st, pl->vbad.p + (size_t)m0 * N, rounds);
-  CU(cudaGetLastError());
-  pl->launches += 1;
-  return 0;
-}
-
-// orders 640 < N <= 1280: two warps per eigenvalue (k_invit2)
-template <int NSH>
-int launch_invit2(stabgpu_plan* pl, int rounds, int m0, int cnt) {
-  const int N = pl->N;
-  const size_t st = (size_t)N * N;
-  const size_t sm = 2 * (size_t)INVIT2_CB * N * sizeof(cplx) + (size_t)INVIT2_PAIRS * N;
-  CU(cudaFuncSetAttribute(k_invit2<NSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  dim3 grid((N + INVIT2_PAIRS * rounds - 1) / (INVIT2_PAIRS * rounds), cnt);
-  k_invit2<NSH><<<grid, INVIT2_PAIRS * 64, sm, pl->stream>>>(pl->A.p + (size_t)m0 * st, st, N, pl->lam.p + (size_t)m0 * N, pl->kr.p + (size_t)m0 * N,
-                                                             pl->hnorm.p + m0, pl->V.p + (size_t)m0 * st, st, pl->vbad.p + (size_t)m0 * N, rounds);
-  CU(cudaGetLastError());
-  pl->launches += 1;
-  return 0;
-}
-
 // Stage 6: right eigenvectors.  evec_mode 1 (default, N <= 1280 and blocked Hessenberg factors available):
 // register-resident inverse iteration -> GEMM back-transformation -> finalize; otherwise the v1 warp kernel.
 // The batch is processed in sub-batches; when the caller registered a host destination (the batch C-ABI calls), the
@@ -438,15 +409,9 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
       pl->launches += 1;
     } else {
       const int rounds = 4;
-      int rc;
-      if (N <= 128) rc = launch_invit<4>(pl, rounds, m0, cnt);
-      else if (N <= 256) rc = launch_invit<8>(pl, rounds, m0, cnt);
-      else if (N <= 384) rc = launch_invit<12>(pl, rounds, m0, cnt);
-      else if (N <= 512) rc = launch_invit<16>(pl, rounds, m0, cnt);
-      else if (N <= 640) rc = launch_invit<20>(pl, rounds, m0, cnt);
-      else if (N <= 1024) rc = launch_invit2<16>(pl, rounds, m0, cnt);
-      else rc = launch_invit2<20>(pl, rounds, m0, cnt);
-      if (rc) return 1;
+      CU(launch_invit(pl->A.p + (size_t)m0 * st, st, N, pl->lam.p + (size_t)m0 * N, pl->kr.p + (size_t)m0 * N, pl->hnorm.p + m0,
+                      pl->V.p + (size_t)m0 * st, st, pl->vbad.p + (size_t)m0 * N, rounds, cnt, s));
+      pl->launches += 1;
       // vectors the fast kernel rejected (no growth / overflow): ZLAEIN's retry vectors, v1 kernel, Hessenberg basis
       k_evec<<<grid_old, warps * 32, sm_old, s>>>(pl->A.p + (size_t)m0 * st, st, N, pl->ilohi.p + 2 * m0, pl->tau.p + (size_t)m0 * N,
                                                   pl->scale.p + (size_t)m0 * N, pl->lam.p + (size_t)m0 * N, pl->kr.p + (size_t)m0 * N,
@@ -581,16 +546,13 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
     HqrLaunch q; q.W = g_tune.W; q.ns_max = g_tune.ns; q.steps_max = g_tune.qr_steps;
     if (q.W - 2 < 2 * q.ns_max - 1 || q.steps_max < 2 * q.ns_max - 1 || q.W - 2 * q.ns_max - 1 < 4)
       return fail("libstabgpu: invalid QR tuning (window too small for the shift count)");
-    size_t sm = hqr_smem_bytes(q);
-    CU(cudaFuncSetAttribute(k_hqr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     long long* prof = nullptr;
     if (g_qrprof_on) {
       if (!g_qrprof_dev) CU(cudaMalloc(&g_qrprof_dev, 16 * sizeof(long long)));
       CU(cudaMemsetAsync(g_qrprof_dev, 0, 16 * sizeof(long long), s));
       prof = g_qrprof_dev;
     }
-    k_hqr<<<np, g_tune.qr_threads, sm, s>>>(Hq, st, N, pl->ilohi.p, pl->w.p, pl->info_qr.p, q, prof, pl->hnorm.p);
-    CU(cudaGetLastError());
+    CU(launch_hqr(Hq, st, N, pl->ilohi.p, pl->w.p, pl->info_qr.p, q, prof, pl->hnorm.p, np, g_tune.qr_threads, s));
   }
   CU(cudaEventRecord(pl->ev[ST_QR + 1], s));
   k_sort<<<np, 256, 0, s>>>(pl->w.p, N, sort_mode, pl->hnorm.p, pl->blkend.p, pl->eig.p, pl->lam.p, pl->kr.p);

@@ -41,7 +41,7 @@ int emu_hqr(cplx* H, int n, int ilo, int ihi, cplx* w, int W, int ns_max, int st
   HqrSmem sh;
   sh.W = W; sh.ldw = W + 1;
   std::vector<cplx> win((size_t)W * (W + 1)), shifts(ns_max), sm((size_t)ns_max * (ns_max + 1));
-  std::vector<Refl> rec((size_t)steps_max * ns_max), cur(2 * ns_max);
+  std::vector<Rot> rec((size_t)steps_max * ns_max), cur(2 * ns_max);
   SmallCtl ctl;
   sh.win = win.data(); sh.rec = rec.data(); sh.steps_max = steps_max; sh.ns_max = ns_max;
   sh.cur = cur.data(); sh.shifts = shifts.data(); sh.sm = sm.data(); sh.ctl = &ctl; sh.prof = nullptr;
