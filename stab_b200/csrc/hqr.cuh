@@ -277,6 +277,10 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
   grp_sync(g);
   const int nbt = (g.nt >= 64) ? 32 : 0;                    // threads reserved for the bulge jobs (first warp)
   const int ntile = ns * (ns - 1) / 2;
+  int jj0 = (g.tid - nbt) - (ntile % (g.nt - nbt)); if (jj0 < 0) jj0 += g.nt - nbt;   // first line job of this thread (loop invariant)
+#ifdef STAB_CHASE_MB
+  long long mb_t0_ = clock64();
+#endif
   for (int t = ta; t < tb; ++t) {
     const Rot* cb = cur + (t & 1) * ns;
     Rot* nb = cur + ((t + 1) & 1) * ns;
@@ -285,6 +289,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
     int bhi = t >> 1; if (bhi > ns - 1) bhi = ns - 1;
     int blo = (t - smax + 1) >> 1; if (blo < 0) blo = 0;     // ceil((t - smax)/2) for t - smax >= 0
     // ---- bulge jobs ------------------------------------------------------------------------
+#ifndef STAB_MB_NOBULGE
     if (g.tid < (nbt ? ns : g.nt)) {
       for (int b = g.tid; b < ns; b += (nbt ? ns : g.nt)) {
         const int s = t - 2 * b;
@@ -316,6 +321,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
         if (more) rec[(t + 1 - ta) * ns + rec_slot(ns, b)] = rn;
       }
     }
+#endif
     // ---- tile and line jobs -----------------------------------------------------------------
     if (blo <= bhi && (nbt == 0 || g.tid >= nbt)) {
       const int klo = kb0 + t - 2 * blo;                     // position of the leading active bulge
@@ -327,6 +333,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
       const int nq = (ns + 3) >> 2;
       const int nline = nL + nR;
       const int w0 = g.tid - nbt, wn = g.nt - nbt;
+#ifndef STAB_MB_NOTILE
       for (int j = w0; j < ntile; j += wn) {
         const int p = j / ns, i = j - p * ns;
         int b, bp;
@@ -340,40 +347,49 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
         apply_right(rr, a00, a01); apply_right(rr, a10, a11);
         q0[0] = a00; q0[1] = a10; q0[lds] = a01; q0[lds + 1] = a11;
       }
-      // line jobs continue the job numbering after the tiles, so the threads without a tile take the first lines
-      const int nlj = nline * nq;
-      int jj = w0 - (ntile % wn); if (jj < 0) jj += wn;
-      for (int u = jj; u < nlj; u += wn) {
-        int q = 0, line = u;                                 // q = u / nline without a division (nq is small)
-        while (line >= nline) { line -= nline; ++q; }        // consecutive threads: consecutive lines (bank-conflict free)
-        if (line < nL) {                                     // column c0 + line: left applications of bulges 4q .. 4q+3
-          cplx* col = S + (c0 + line) * lds;
+#endif
+      // Line jobs continue the job numbering after the tiles, so the threads without a tile take the first lines.  The
+      // column jobs (left applications) of every quarter come first, then the row jobs: a warp holds one kind except at
+      // the single boundary, and since [x1 x2] G^H is G(c, conj s) applied to [x1; x2], both kinds run the SAME code with
+      // the sign of Im s and the element stride selected per job -- no divergent branch.  All loads of a job are issued
+      // before its arithmetic (four independent rotations), all stores after it.
+      const int nCol = nL * nq, nlj = nCol + nR * nq;
+#ifdef STAB_MB_NOLINE
+      if (false)
+#endif
+      for (int u = jj0; u < nlj; u += wn) {
+        const bool iscol = u < nCol;
+        int v = iscol ? u : u - nCol;
+        const int len = iscol ? nL : nR;
+        int q = 0;
+        while (v >= len) { v -= len; ++q; }                  // q = v / len without a division (nq is small); consecutive threads: consecutive lines
+        cplx* base = iscol ? S + (c0 + v) * lds : S + v;
+        const int str = iscol ? 1 : lds;
+        const double sgn = iscol ? 1.0 : -1.0;
+        cplx x1[4], x2[4]; Rot r[4]; bool on[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int b = 4 * q + e;
-            if (b >= blo && b <= bhi) {
-              const int k = kb0 + t - 2 * b;
-              cplx x1 = col[k], x2 = col[k + 1];
-              apply_left(cb[b], x1, x2);
-              col[k] = x1; col[k + 1] = x2;
-            }
-          }
-        } else {                                             // row (line - nL): right applications of bulges 4q .. 4q+3
-          cplx* row = S + (line - nL);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int b = 4 * q + e;
-            if (b >= blo && b <= bhi) {
-              const int k = kb0 + t - 2 * b;
-              cplx x1 = row[k * lds], x2 = row[(k + 1) * lds];
-              apply_right(cb[b], x1, x2);
-              row[k * lds] = x1; row[(k + 1) * lds] = x2;
-            }
-          }
+        for (int e = 0; e < 4; ++e) {
+          const int b = 4 * q + e;
+          on[e] = b >= blo && b <= bhi;
+          const int k = kb0 + t - 2 * (on[e] ? b : blo);
+          x1[e] = base[k * str]; x2[e] = base[(k + 1) * str];
+          r[e] = cb[on[e] ? b : blo];
+          r[e].s.im *= sgn;
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) apply_left(r[e], x1[e], x2[e]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (on[e]) { const int k = kb0 + t - 2 * (4 * q + e); base[k * str] = x1[e]; base[(k + 1) * str] = x2[e]; }
       }
     }
+#ifdef STAB_CHASE_MB
+    if ((g.tid & 31) == 0) { long long now_ = clock64(); g_chase_busy[g.tid >> 5] += now_ - mb_t0_; }
+#endif
     grp_sync(g);
+#ifdef STAB_CHASE_MB
+    mb_t0_ = clock64();
+#endif
   }
 }
 
