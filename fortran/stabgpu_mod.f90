@@ -21,6 +21,26 @@ module stabgpu_mod
        integer(c_int), value :: device
      end function stabgpu_init
 
+     !> the drop-in case: one serial Fortran process, every GPU of the box behind each *_batch call
+     integer(c_int) function stabgpu_init_multi(max_devices, ndev_used) bind(C, name='stabgpu_init_multi')
+       import :: c_int
+       integer(c_int), value       :: max_devices          ! <= 0: all visible devices
+       integer(c_int), intent(out) :: ndev_used
+     end function stabgpu_init_multi
+
+     !> optional: page-lock a caller array once (c_loc(evec), bytes) so the eigenvectors arrive by direct DMA;
+     !> without it a pageable destination is served through the library's pinned staging ring
+     integer(c_int) function stabgpu_host_register(ptr, bytes) bind(C, name='stabgpu_host_register')
+       import :: c_int, c_ptr, c_size_t
+       type(c_ptr), value       :: ptr
+       integer(c_size_t), value :: bytes
+     end function stabgpu_host_register
+
+     integer(c_int) function stabgpu_host_unregister(ptr) bind(C, name='stabgpu_host_unregister')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ptr
+     end function stabgpu_host_unregister
+
      integer(c_int) function stabgpu_finalize() bind(C, name='stabgpu_finalize')
        import :: c_int
      end function stabgpu_finalize
@@ -52,6 +72,23 @@ module stabgpu_mod
        type(c_ptr), value          :: evec
        integer(c_int), intent(out) :: info(*)
      end function stabgpu_spatial_batch
+
+     !> stage (4): one mode per sweep point polished from a shift sigma(p); kind 1 temporal (omega), 2 spatial (alpha)
+     integer(c_int) function stabgpu_polish_batch(kind, p, vm, g2vm, g22vm, deta, d2eta, h5, npts, s1, s2, Re_pt, Ma_pt, &
+                                                  sigma, x0, max_iters, tol, lambda, x, resid, iters)                   &
+                                                  bind(C, name='stabgpu_polish_batch')
+       import :: c_int, c_double, c_double_complex, c_ptr, stabgpu_params
+       integer(c_int), value       :: kind
+       type(stabgpu_params), intent(in) :: p
+       real(c_double), intent(in)  :: vm(*), deta(*), d2eta(*)
+       type(c_ptr), value          :: g2vm, g22vm, h5, Re_pt, Ma_pt, x0, x   ! c_null_ptr when absent
+       integer(c_int), value       :: npts, max_iters
+       complex(c_double_complex), intent(in)  :: s1(*), s2(*), sigma(*)
+       real(c_double), value       :: tol
+       complex(c_double_complex), intent(out) :: lambda(*)
+       real(c_double), intent(out) :: resid(*)
+       integer(c_int), intent(out) :: iters(*)
+     end function stabgpu_polish_batch
 
      integer(c_int) function stabgpu_temporal_polish(p, vm, g2vm, g22vm, deta, d2eta, alpha, beta, sigma, x0, &
                                                      max_iters, tol, lambda, x, resid, iters)                 &

@@ -330,7 +330,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
       int nL = wsz - c0; if (nL < 0) nL = 0;
       if (c0 > ilast) nL = 0;
       const int nR = khi;                                    // right-only rows 0 .. khi-1
-      const int nq = (ns + 3) >> 2;
+      const int nq = (ns + LINE_ROT - 1) / LINE_ROT;
       const int nline = nL + nR;
       const int w0 = g.tid - nbt, wn = g.nt - nbt;
 #ifndef STAB_MB_NOTILE
@@ -366,10 +366,10 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
         cplx* base = iscol ? S + (c0 + v) * lds : S + v;
         const int str = iscol ? 1 : lds;
         const double sgn = iscol ? 1.0 : -1.0;
-        cplx x1[4], x2[4]; Rot r[4]; bool on[4];
+        cplx x1[LINE_ROT], x2[LINE_ROT]; Rot r[LINE_ROT]; bool on[LINE_ROT];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int b = 4 * q + e;
+        for (int e = 0; e < LINE_ROT; ++e) {
+          const int b = LINE_ROT * q + e;
           on[e] = b >= blo && b <= bhi;
           const int k = kb0 + t - 2 * (on[e] ? b : blo);
           x1[e] = base[k * str]; x2[e] = base[(k + 1) * str];
@@ -377,10 +377,10 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
           r[e].s.im *= sgn;
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) apply_left(r[e], x1[e], x2[e]);
+        for (int e = 0; e < LINE_ROT; ++e) apply_left(r[e], x1[e], x2[e]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (on[e]) { const int k = kb0 + t - 2 * (4 * q + e); base[k * str] = x1[e]; base[(k + 1) * str] = x2[e]; }
+        for (int e = 0; e < LINE_ROT; ++e)
+          if (on[e]) { const int k = kb0 + t - 2 * (LINE_ROT * q + e); base[k * str] = x1[e]; base[(k + 1) * str] = x2[e]; }
       }
     }
 #ifdef STAB_CHASE_MB
