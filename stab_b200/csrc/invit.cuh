@@ -16,6 +16,7 @@
 // the back-transformation by Q is a tensor-core GEMM (k_bt_* kernels), then k_vec_finalize.
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 #ifndef STAB_EMU
 namespace stab {
@@ -121,8 +122,8 @@ struct InvitSlot {
     for (int bq = 3; bq >= 0; --bq) {
       const int B = 4 * SB + bq;
       if (8 * B > n - 1) continue;                       // block above the matrix (uniform)
-      cp_async_wait<0>();
-      __syncthreads();                                   // block B landed; everyone left block B+1
+      prefetch.wait(buf);                                // block B landed (transaction barrier of its buffer)
+      __syncthreads();                                   // everyone left block B+1
       if (B > 0) prefetch(B - 1, buf ^ 1);
       const cplx* tile = sH + (size_t)buf * INVIT_CB * n;
       for (int q = INVIT_CB - 1; q >= 0; --q) {
@@ -155,6 +156,10 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
   const double smlnum = SD_SAFMIN * ((double)n / SD_ULP);
   const double eps3 = fmax(SD_ULP * hnorm[p], smlnum);
   const double growto = 0.1 / sqrt((double)n);
+  __shared__ uint64_t bars[2];                              // transaction barriers of the two staging buffers
+  if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  __syncthreads();
+  unsigned par = 0u;                                        // phase parity of the two barriers (bits 0, 1), tracked by every thread
 
   for (int rd = 0; rd < rounds; ++rd) {
     const int e = (blockIdx.x * rounds + rd) * INVIT_WARPS + wid;
@@ -168,17 +173,30 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
     cplx cdiag = mk(0.0, 0.0), ydiag = mk(0.0, 0.0);
 
     // block B covers steps k = 8B+7 .. 8B, i.e. columns k-1 = 8B+6 .. 8B-1, rows 0..k of each;
-    // tile column q <-> step k = 8B+q
-    auto prefetch = [&](int B, int bufi) {
-      cplx* dst = sH + (size_t)bufi * INVIT_CB * n;
-      for (int q = 0; q < INVIT_CB; ++q) {
-        const int k = 8 * B + q;
-        if (k < 1 || k > n - 1) continue;
-        const cplx* src = H + (size_t)(k - 1) * n;
-        for (int r = threadIdx.x; r <= k; r += blockDim.x) cp_async16(dst + (size_t)q * n + r, src + r);
+    // tile column q <-> step k = 8B+q.  Every column is one contiguous run of (k+1) entries: ONE thread issues one bulk
+    // copy (TMA engine, cp.async.bulk) per column with completion on the buffer's transaction barrier -- no per-thread
+    // 16-byte cp.async and address arithmetic (that loop was 6 % of the kernel's instructions).
+    struct Stager {
+      const cplx* H; cplx* sH; uint64_t* bars; unsigned* parity; int n;
+      __device__ void operator()(int B, int bufi) const {
+        if (threadIdx.x != 0) return;
+        cplx* dst = sH + (size_t)bufi * INVIT_CB * n;
+        unsigned bytes = 0;
+        for (int q = 0; q < INVIT_CB; ++q) {
+          const int k = 8 * B + q;
+          if (k >= 1 && k <= n - 1) bytes += (unsigned)(k + 1) * 16u;
+        }
+        fence_async_smem();                                  // the buffer may have been written by generic stores (parked vectors)
+        mbar_arrive_expect_tx(bars + bufi, bytes);
+        for (int q = 0; q < INVIT_CB; ++q) {
+          const int k = 8 * B + q;
+          if (k < 1 || k > n - 1) continue;
+          bulk_g2s(dst + (size_t)q * n, H + (size_t)(k - 1) * n, (unsigned)(k + 1) * 16u, bars + bufi);
+        }
       }
-      cp_async_commit();
+      __device__ void wait(int bufi) const { mbar_wait(bars + bufi, (*parity >> bufi) & 1u); *parity ^= 1u << bufi; }
     };
+    Stager prefetch{H, sH, bars, &par, n};
     if (live) {                                             // start: carried column = column m-1 of H - lam I
       const cplx* hc = H + (size_t)(m - 1) * n;
 #pragma unroll
@@ -311,8 +329,8 @@ struct Invit2Slot {
     for (int bq = 32 / INVIT2_CB - 1; bq >= 0; --bq) {
       const int B = (32 / INVIT2_CB) * SBG + bq;
       if (INVIT2_CB * B > n - 1) continue;                 // block above the matrix (uniform)
-      cp_async_wait<0>();
-      __syncthreads();                                     // block B landed; everyone left block B+1
+      prefetch.wait(buf);                                  // block B landed (transaction barrier of its buffer)
+      __syncthreads();                                     // everyone left block B+1
       if (B > 0) prefetch(B - 1, buf ^ 1);
       const cplx* tile = sH + (size_t)buf * INVIT2_CB * n;
       for (int q = INVIT2_CB - 1; q >= 0; --q) {
@@ -367,6 +385,10 @@ k_invit2(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restr
   const double smlnum = SD_SAFMIN * ((double)n / SD_ULP);
   const double eps3 = fmax(SD_ULP * hnorm[p], smlnum);
   const double growto = 0.1 / sqrt((double)n);
+  __shared__ uint64_t bars[2];                              // transaction barriers of the two staging buffers
+  if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  __syncthreads();
+  unsigned par = 0u;
 
   for (int rd = 0; rd < rounds; ++rd) {
     const int e = (blockIdx.x * rounds + rd) * INVIT2_PAIRS + pi;
@@ -379,17 +401,29 @@ k_invit2(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restr
     unsigned flags = 0u;
     cplx cdiag = mk(0.0, 0.0), ydiag = mk(0.0, 0.0);
 
-    // block B covers steps k = 4B+3 .. 4B, i.e. columns k-1, rows 0..k of each; tile column q <-> step k = 4B+q
-    auto prefetch = [&](int B, int bufi) {
-      cplx* dst = sH + (size_t)bufi * INVIT2_CB * n;
-      for (int q = 0; q < INVIT2_CB; ++q) {
-        const int k = INVIT2_CB * B + q;
-        if (k < 1 || k > n - 1) continue;
-        const cplx* src = H + (size_t)(k - 1) * n;
-        for (int r = threadIdx.x; r <= k; r += blockDim.x) cp_async16(dst + (size_t)q * n + r, src + r);
+    // block B covers steps k = 4B+3 .. 4B, i.e. columns k-1, rows 0..k of each; tile column q <-> step k = 4B+q; one
+    // bulk copy (TMA engine) per column, issued by one thread, completion on the buffer's transaction barrier
+    struct Stager {
+      const cplx* H; cplx* sH; uint64_t* bars; unsigned* parity; int n;
+      __device__ void operator()(int B, int bufi) const {
+        if (threadIdx.x != 0) return;
+        cplx* dst = sH + (size_t)bufi * INVIT2_CB * n;
+        unsigned bytes = 0;
+        for (int q = 0; q < INVIT2_CB; ++q) {
+          const int k = INVIT2_CB * B + q;
+          if (k >= 1 && k <= n - 1) bytes += (unsigned)(k + 1) * 16u;
+        }
+        fence_async_smem();
+        mbar_arrive_expect_tx(bars + bufi, bytes);
+        for (int q = 0; q < INVIT2_CB; ++q) {
+          const int k = INVIT2_CB * B + q;
+          if (k < 1 || k > n - 1) continue;
+          bulk_g2s(dst + (size_t)q * n, H + (size_t)(k - 1) * n, (unsigned)(k + 1) * 16u, bars + bufi);
+        }
       }
-      cp_async_commit();
+      __device__ void wait(int bufi) const { mbar_wait(bars + bufi, (*parity >> bufi) & 1u); *parity ^= 1u << bufi; }
     };
+    Stager prefetch{H, sH, bars, &par, n};
     if (live) {                                             // start: carried column = column m-1 of H - lam I
       const cplx* hc = H + (size_t)(m - 1) * n;
 #pragma unroll
