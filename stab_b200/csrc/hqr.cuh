@@ -20,6 +20,10 @@
 
 namespace stab {
 
+#ifndef LINE_ROT
+#define LINE_ROT 4          // rotations (consecutive bulges) per line job of chase_tiles (2 and 8 measured: no better)
+#endif
+
 // A bulge step is a complex plane rotation G = [c s; -conj(s) c] (c real, ZLARTG's form) rather than ZLAHQR's
 // 2-element Householder reflector: the same unitary similarity up to a phase, but 12 FMA-class operations per
 // updated pair in FOUR independent chains of depth 3 (the reflector form is 14 operations in two chains of depth
