@@ -17,6 +17,7 @@
 // Eigenvalues only => all updates are restricted to the active block [L, I].
 #pragma once
 #include "common.cuh"
+#include "hessenberg.cuh"   // cta_zlarfg
 
 namespace stab {
 
@@ -242,14 +243,17 @@ SD_DEV void chase(const Grp& g, cplx* S, int lds, int g0, int rlo, int chi, int 
 //     reflector b on both columns, right with reflector b' on both rows;
 //   * line jobs: columns right of the chain (left applications only) and rows above it (right
 //     applications only), four consecutive bulges (8 contiguous entries) per job.
-// S is the wsz x wsz window with global origin g0 (rows above the active block are never inside:
-// g0 >= L).  cur holds 2*ns reflectors.  rec receives reflector (t, b) at (t-ta)*ns + b.
+// S is the wsz x wsz window with global origin g0 (g0 <= L).  Everything inside the window is updated: columns right
+// of the active block and rows above it too (they exist only when the caller wants the Schur form of the window, not
+// just its eigenvalues), and the right applications extend upwards to local row rtop <= 0 -- the rows rtop..-1 of the
+// same array hold a matrix that accumulates the rotations (the stacked [Z; T] layout of the deflation window).
+// cur holds 2*ns reflectors.  rec receives reflector (t, b) at (t-ta)*ns + b.
 // ---------------------------------------------------------------------------------------------
 SD_DEV Rot zero_refl() { Rot r = rot_identity(); return r; }
 
 template <int NSC>
 SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, int I,
-                        const cplx* shifts, int ns_rt, int ta, int tb, Rot* rec, Rot* cur) {
+                        const cplx* shifts, int ns_rt, int ta, int tb, Rot* rec, Rot* cur, int rtop = 0) {
   const int ns = NSC ? NSC : ns_rt;                          // compile-time shift count when known (index arithmetic by shifts)
   const int smax = I - 1 - L;
   const int kb0 = L - g0;                                   // local position of a bulge at s = 0
@@ -332,8 +336,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
       const int khi = kb0 + t - 2 * bhi;                     // position of the trailing active bulge
       const int c0 = klo + 2;                                // first left-only column
       int nL = wsz - c0; if (nL < 0) nL = 0;
-      if (c0 > ilast) nL = 0;
-      const int nR = khi;                                    // right-only rows 0 .. khi-1
+      const int nR = khi - rtop;                             // right-only rows rtop .. khi-1
       const int nq = (ns + LINE_ROT - 1) / LINE_ROT;
       const int nline = nL + nR;
       const int w0 = g.tid - nbt, wn = g.nt - nbt;
@@ -367,7 +370,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
         const int len = iscol ? nL : nR;
         int q = 0;
         while (v >= len) { v -= len; ++q; }                  // q = v / len without a division (nq is small); consecutive threads: consecutive lines
-        cplx* base = iscol ? S + (c0 + v) * lds : S + v;
+        cplx* base = iscol ? S + (c0 + v) * lds : S + (v + rtop);
         const int str = iscol ? 1 : lds;
         const double sgn = iscol ? 1.0 : -1.0;
         cplx x1[LINE_ROT], x2[LINE_ROT]; Rot r[LINE_ROT]; bool on[LINE_ROT];
@@ -443,43 +446,99 @@ SD_DEV cplx wilkinson_shift(cplx h11, cplx h12, cplx h21, cplx h22) {
   return t;
 }
 
-struct SmallCtl { int L; int pad; cplx shift; };
+// Both eigenvalues of [h11 h12; h21 h22], l1 the one closer to h22 (Wilkinson's choice): mid +- sqrt(dlt^2 + h12 h21) with
+// ONE complex square root built on rsqrt -- no hypot, no division (each a ~250-cycle dependent sequence on the one
+// thread every other thread of the group is waiting for; the LAPACK-style wilkinson_shift above costs ~5000 cycles).
+// The cancellation of the direct formula perturbs a shift by O(eps |h11 - h22|), which the iteration does not notice.
+SD_DEV void eig2x2_fast(cplx h11, cplx h12, cplx h21, cplx h22, cplx& l1, cplx& l2) {
+  const cplx mid = mk(0.5 * (h11.re + h22.re), 0.5 * (h11.im + h22.im));
+  const cplx dlt = mk(0.5 * (h11.re - h22.re), 0.5 * (h11.im - h22.im));
+  const cplx disc = dlt * dlt + h12 * h21;
+  const double a2 = fma(disc.re, disc.re, disc.im * disc.im);
+  cplx r;
+  if (!(a2 > 1.0e-280 && a2 < 1.0e280)) {
+    r = csqrt_(disc);                                       // out of the safe range of the squares (or zero / NaN)
+  } else {
+#ifdef STAB_EMU
+    const double m = sqrt(a2);
+    const double t = 0.5 * (m + fabs(disc.re)), it = 1.0 / sqrt(t);
+#else
+    const double m = a2 * rsqrt(a2);
+    const double t = 0.5 * (m + fabs(disc.re)), it = rsqrt(t);
+#endif
+    const double sr = t * it, si = 0.5 * disc.im * it;
+    r = (disc.re >= 0.0) ? mk(sr, si) : mk(fabs(si), disc.im >= 0.0 ? sr : -sr);
+  }
+  // l - h22 = dlt +- r: take the smaller one
+  const double dot = dlt.re * r.re + dlt.im * r.im;
+  if (dot > 0.0) r = -r;
+  l1 = mid + r; l2 = mid - r;
+}
 
-// All eigenvalues of the m x m upper Hessenberg matrix S (shared memory), single-shift QR.
-// Returns the number of eigenvalues that failed to converge (0 = success); converged ones are in
-// wout[...], for failures wout holds the current diagonal.
-SD_DEV int smem_hqr(const Grp& g, cplx* S, int lds, int m, cplx* wout, SmallCtl* ctl, Rot* cur, Rot* rec) {
+struct SmallCtl { int L; int pad; cplx shift[2]; };
+
+// Early termination of the Schur factorisation of a deflation window (smem_hqr<true>): the eigenvalues converge from
+// the bottom of the window upwards, and column j of Z is final once position j has converged, so the deflation test of
+// aggressive early deflation -- |s| |Z(0,j)| <= max(smlnum, ulp |T(j,j)|) -- is taken the moment position j converges.
+// Without reordering the deflation ends at the first failure; the factorisation then goes on only for the `want`
+// eigenvalues the next sweep uses as shifts, and not at all when nd >= nd_skip (another deflation step follows).
+struct AedStop { double s1, smlnum; int nd_skip, want; };
+#ifdef STAB_EMU_COUNT
+static long long g_emu_cnt[8];
+#endif
+
+SD_DEV void grp_amax(int* p, int v) {              // shared-memory integer max (a plain max under emulation)
+#ifdef STAB_EMU
+  if (v > *p) *p = v;
+#else
+  atomicMax(p, v);
+#endif
+}
+
+// All eigenvalues of the m x m upper Hessenberg matrix S (shared memory) by shifted QR.  A QR iteration chases a chain
+// of TWO bulges whose shifts are the two eigenvalues of the trailing 2 x 2 block (one bulge with ZLAHQR's Wilkinson
+// shift on blocks of order < 4, and for the exceptional shifts): half the time steps of single-shift sweeps, each of
+// them with one barrier (chase_tiles).  The deflation scan is done by the whole group, one subdiagonal per thread.
+// WANTT: S is taken to its Schur form -- the rotations act on the whole m x m matrix, not just the active block -- and
+// are accumulated from the right into the zrows rows stored directly above S in the same array (rows -zrows..-1).
+// Returns the number of eigenvalues that failed to converge (0 = success); converged ones are in wout[...], for
+// failures wout holds the current diagonal.
+template <bool WANTT>
+SD_DEV int smem_hqr(const Grp& g, cplx* S, int lds, int m, int zrows, cplx* wout, SmallCtl* ctl, Rot* cur, Rot* rec,
+                    const AedStop* stop = nullptr, int* ns_out = nullptr, int* istop_out = nullptr) {
   const double smlnum = SD_SAFMIN * ((double)m / SD_ULP);
   int I = m - 1;
   int its = 0;
   const int itmax = 30 * (m > 10 ? m : 10);
   int total = 0;
   SmemAt at; at.S = S; at.lds = lds;
-  while (I >= 0) {
-    if (g.tid == 0) {
-      int L = 0;
-      for (int k = I; k >= 1; --k) {
-        if (negligible_subdiag(at, k, 0, m - 1, smlnum)) { L = k; break; }
-      }
-      if (L > 0) S[L + (L - 1) * lds] = mk(0.0, 0.0);
-      ctl->L = L;
-      if (L < I) {
-        cplx t;
-        if (its == 10) {
-          t = mk(0.75 * fabs(S[L + 1 + L * lds].re), 0.0) + S[L + L * lds];
-        } else if (its == 20) {
-          t = mk(0.75 * fabs(S[I + (I - 1) * lds].re), 0.0) + S[I + I * lds];
-        } else {
-          t = wilkinson_shift(S[I - 1 + (I - 1) * lds], S[I - 1 + I * lds], S[I + (I - 1) * lds], S[I + I * lds]);
-        }
-        ctl->shift = t;
-      } else {
-        wout[I] = S[I + I * lds];
-      }
-    }
+  int ns_und = -1, ilow = -1;                  // undeflated count once the deflation test has failed; stop when I <= ilow
+  while (I > ilow) {
+    if (g.tid == 0) ctl->L = 0;
+    grp_sync(g);
+    for (int k = 1 + g.tid; k <= I; k += g.nt)
+      if (negligible_subdiag(at, k, 0, m - 1, smlnum)) grp_amax(&ctl->L, k);
     grp_sync(g);
     const int L = ctl->L;
-    if (L >= I) { I -= 1; its = 0; grp_sync(g); continue; }
+    if (L >= I) {
+      if (g.tid == 0) {
+        if (L > 0) S[L + (L - 1) * lds] = mk(0.0, 0.0);
+        wout[I] = S[I + I * lds];
+      }
+      if (WANTT && stop && ns_und < 0) {       // deflation test of the eigenvalue that has just converged (uniform)
+        double foo = cabs1(S[I + I * lds]);
+        if (foo == 0.0) foo = stop->s1;
+        if (!(stop->s1 * cabs1(S[-zrows + I * lds]) <= fmax(stop->smlnum, SD_ULP * foo))) {
+          ns_und = I + 1;
+          const int nd = m - ns_und;
+          ilow = (nd >= stop->nd_skip) ? I : ns_und - 1 - stop->want;
+          if (ilow < -1) ilow = -1;
+        }
+      }
+      I -= 1; its = 0;
+      grp_sync(g);
+      continue;
+    }
     if (total++ >= itmax) {
       // give up: report the diagonal for what is left
       for (int k = g.tid; k <= I; k += g.nt) wout[k] = S[k + k * lds];
@@ -487,23 +546,47 @@ SD_DEV int smem_hqr(const Grp& g, cplx* S, int lds, int m, cplx* wout, SmallCtl*
       return I + 1;
     }
     its += 1;
-    // one bulge through the active block [L, I] with ONE barrier per step (chase_tiles on the block as its own window;
-    // rows above and columns right of the block are not needed for eigenvalues); `rec` is scratch here
-    chase_tiles<0>(g, S + L + (size_t)L * lds, lds, L, I - L + 1, L, I, &ctl->shift, 1, 0, I - L, rec, cur);
+    const bool exceptional = (its == 10 || its == 20);
+    const int nsh = (!exceptional && I - L + 1 >= 4) ? 2 : 1;
+    if (g.tid == 0) {
+      if (L > 0) S[L + (L - 1) * lds] = mk(0.0, 0.0);
+      cplx t;
+      if (its == 10) {
+        t = mk(0.75 * fabs(S[L + 1 + L * lds].re), 0.0) + S[L + L * lds];
+      } else if (its == 20) {
+        t = mk(0.75 * fabs(S[I + (I - 1) * lds].re), 0.0) + S[I + I * lds];
+      } else {
+        eig2x2_fast(S[I - 1 + (I - 1) * lds], S[I - 1 + I * lds], S[I + (I - 1) * lds], S[I + I * lds], t, ctl->shift[1]);
+      }
+      ctl->shift[0] = t;
+    }
+    grp_sync(g);
+    const int T = (I - L) + 2 * nsh - 2;
+#ifdef STAB_EMU_COUNT
+    g_emu_cnt[WANTT ? 0 : 2] += 1; g_emu_cnt[WANTT ? 1 : 3] += T; if (nsh == 1) g_emu_cnt[4] += 1;
+#endif
+#ifdef STAB_MB_COUNT
+    if (g.tid == 0 && blockIdx.x == 0) { g_steps[0] += 1; g_steps[1] += T; }
+#endif
+    if (WANTT) chase_tiles<0>(g, S, lds, 0, m, L, I, ctl->shift, nsh, 0, T, rec, cur, -zrows);
+    else chase_tiles<0>(g, S + L + (size_t)L * lds, lds, L, I - L + 1, L, I, ctl->shift, nsh, 0, T, rec, cur, 0);
   }
+  if (ns_out) *ns_out = ns_und < 0 ? 0 : ns_und;
+  if (istop_out) *istop_out = I;
   return 0;
 }
 
 struct HqrSmem {
-  cplx* win;     // W * ldw
+  cplx* win;     // W * ldw; also the stacked [Z; T] arrays of the deflation window: (2 nw + 1) * nw <= W * ldw
   int ldw, W;
+  int nw, nibble; // deflation window (0: no aggressive early deflation) and ZLAQR0's NIBBLE (percent)
   Rot* rec;     // steps_max * ns_max
   int steps_max, ns_max;
   Rot* cur;     // 2 * ns_max (double-buffered by chase_tiles)
   cplx* shifts;  // ns_max
   cplx* sm;      // ns_max * (ns_max + 1)   trailing block for the shift computation
   SmallCtl* ctl;
-  long long* prof;   // optional cycle counters (debug), in SHARED memory (copied out by the kernel at the end): scan, shifts, window io, chase, left slab, right slab, small blocks, #sweeps, #passes
+  long long* prof;   // optional cycle counters (debug), in SHARED memory (copied out by the kernel at the end): 0 scan, 1 shifts, 2 window io, 3 chase, 4 slabs, 5 -, 6 small blocks, 7 #sweeps, 8 #passes, 9 sweeps (outer clock), 10 AED write-back + slab, 11 #AED, 12 #deflated by AED, 13 AED Schur, 14 AED count + restore, 15 AED (outer clock)
 };
 
 #if defined(STAB_EMU)
@@ -841,6 +924,180 @@ SD_DEV void sweep_multishift(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Aggressive early deflation (Braman, Byers, Mathias; ZLAQR3's logic for eigenvalues only) on the trailing jw x jw
+// window of the active block [L, I], kw = I-jw+1 > L, with s = H(kw, kw-1):
+//   1. T = Schur form of the window, Z its Schur vectors (smem_hqr<true> on the stacked [Z; T] shared-memory array);
+//   2. in the basis Z the window couples to the rest of the block only through the spike s conj(Z(0, :)); the
+//      trailing eigenvalues whose spike entries are negligible (|s| |Z(0,j)| <= max(smlnum, ulp |T(j,j)|)) are
+//      deflated -- nd of them, counted from the bottom up to the first one that fails (no reordering of the Schur form:
+//      on the reference's operators the count without ZTREXC is within a few per cent of the count with it), which
+//      lets step 1 stop early (AedStop): only the deflated eigenvalues and the next sweep's shifts are converged;
+//   3. if nd > 0 the undeflated part (ns = jw - nd) returns to Hessenberg form: a reflector takes the spike to a multiple
+//      of e1, ZGEHD2 on the ns x ns block (in shared memory, Z accumulating), H(kw, kw-1) = s conj(Z(0,0)), and the
+//      columns of the block above the window are multiplied by Z(:, 0:ns) (aed_slab).  The coupling block T(0:ns, ns:jw)
+//      is dropped: eigenvalues only.
+// The diagonal of T(0:ns, 0:ns) (before step 3) are the shifts of the next sweep (ZLAQR0), written to sh.shifts --
+// nshift of them (0: none usable, the caller computes its own); fewer than nshift_want distinct ones are cycled.
+// Returns nd; the deflated eigenvalues are stored in w[kw+ns .. I].  H is untouched when nd == 0.
+// ---------------------------------------------------------------------------------------------
+template <int KH>
+SD_NOINLINE void aed_slab(int tid, int nt, cplx* H, int ldh, int L, int kw, int jw, int ns, const cplx* Zs, int lds) {
+  // H(L:kw-1, kw:kw+ns-1) = H(L:kw-1, kw:kw+jw-1) Z(:, 0:ns-1), in place: a row is held in registers, half of it per
+  // lane of a lane pair (KH entries each, 2 KH >= jw), the partial sums meet by one shuffle per output; a store of
+  // output j happens after the shuffle, i.e. after BOTH lanes have loaded (and consumed) their whole half row.
+#ifdef STAB_EMU
+  (void)tid; (void)nt;
+  cplx row[2 * KH];
+  for (int r = L; r < kw; ++r) {
+    for (int k = 0; k < jw; ++k) row[k] = H[r + (size_t)(kw + k) * ldh];
+    for (int j = 0; j < ns; ++j) {
+      cplx acc = mk(0.0, 0.0);
+      for (int k = 0; k < jw; ++k) fma_acc(acc, row[k], Zs[k + j * lds]);
+      H[r + (size_t)(kw + j) * ldh] = acc;
+    }
+  }
+#else
+  const int part = tid & 1, k0 = part * KH;
+  const int rows_per_round = nt >> 1;
+  for (int r0 = L; r0 < kw; r0 += rows_per_round) {
+    const int r = r0 + (tid >> 1);
+    const bool act = r < kw;
+    cplx a[KH];
+#pragma unroll
+    for (int i = 0; i < KH; ++i) a[i] = (act && k0 + i < jw) ? H[r + (size_t)(kw + k0 + i) * ldh] : mk(0.0, 0.0);
+    for (int j = 0; j < ns; j += 2) {
+      const int j1 = (j + 1 < ns) ? j + 1 : j;
+      const cplx* z0 = Zs + k0 + j * lds;
+      const cplx* z1 = Zs + k0 + j1 * lds;
+      cplx acc0 = mk(0.0, 0.0), acc1 = mk(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < KH; ++i) { fma_acc(acc0, a[i], z0[i]); fma_acc(acc1, a[i], z1[i]); }
+      acc0.re += __shfl_xor_sync(0xffffffffu, acc0.re, 1); acc0.im += __shfl_xor_sync(0xffffffffu, acc0.im, 1);
+      acc1.re += __shfl_xor_sync(0xffffffffu, acc1.re, 1); acc1.im += __shfl_xor_sync(0xffffffffu, acc1.im, 1);
+      if (act) {
+        if (part == 0) H[r + (size_t)(kw + j) * ldh] = acc0;
+        else if (j + 1 < ns) H[r + (size_t)(kw + j + 1) * ldh] = acc1;
+      }
+    }
+  }
+#endif
+}
+
+// One Householder step of the return to Hessenberg form on the stacked [Z; T] array: P = I - tau v v^H acts on the
+// indices j0 .. ns-1 (v in shared memory, v[0] = 1): T := P^H T P on the leading ns x ns block, Z := Z P.
+SD_DEV void aed_reflect(const Cta& c, cplx* Zs, int lds, int jw, int ns, int j0, const cplx* v, cplx tau) {
+  const int len = ns - j0;
+  cplx* Ts = Zs + jw;
+  // right application on the stacked rows (Z: all jw rows, T: rows 0..ns-1), columns j0..ns-1; a thread owns a row
+  for (int q = c.tid; q < jw + ns; q += c.nt) {
+    cplx* row = Zs + q + (size_t)j0 * lds;
+    cplx x0 = mk(0.0, 0.0), x1 = mk(0.0, 0.0);
+    int i = 0;
+    for (; i + 1 < len; i += 2) { fma_acc(x0, row[(size_t)i * lds], v[i]); fma_acc(x1, row[(size_t)(i + 1) * lds], v[i + 1]); }
+    if (i < len) fma_acc(x0, row[(size_t)i * lds], v[i]);
+    const cplx x = (x0 + x1) * tau;
+    for (i = 0; i < len; ++i) fms_acc(row[(size_t)i * lds], x, conj(v[i]));
+  }
+  cta_sync();
+  // left application on T(j0:ns-1, j0':ns-1); a thread owns a column.  (For j0 >= 1 the columns left of j0 are already
+  // reduced: column j0-1 holds the reflector's source and is set by the caller.)
+  const cplx tauc = conj(tau);
+  for (int col = j0 + c.tid; col < ns; col += c.nt) {
+    cplx* cp = Ts + j0 + (size_t)col * lds;
+    cplx y0 = mk(0.0, 0.0), y1 = mk(0.0, 0.0);
+    int i = 0;
+    for (; i + 1 < len; i += 2) { fma_acc_conj(y0, v[i], cp[i]); fma_acc_conj(y1, v[i + 1], cp[i + 1]); }
+    if (i < len) fma_acc_conj(y0, v[i], cp[i]);
+    const cplx y = (y0 + y1) * tauc;
+    for (i = 0; i < len; ++i) fms_acc(cp[i], v[i], y);
+  }
+  cta_sync();
+}
+
+SD_DEV int aed(const Cta& c, const HqrSmem& sh, cplx* H, int ldh, int L, int I, int jw, double smlnum, cplx* w,
+               int nshift_want, int* nshift) {
+  Grp g; g.tid = c.tid; g.nt = c.nt; g.warp = false;
+  const int kw = I - jw + 1;
+  const int lds = 2 * jw + 1;
+  cplx* Zs = sh.win;                  // Z(r, c) = Zs[r + c lds]
+  cplx* Ts = sh.win + jw;             // T(r, c) = Ts[r + c lds]
+  const cplx s = (kw > L) ? H[kw + (size_t)(kw - 1) * ldh] : mk(0.0, 0.0);
+  HQR_PROF_START();
+  HQR_COUNT(11);
+  for (int q = c.tid; q < jw * jw; q += c.nt) {
+    const int col = q / jw, row = q - col * jw;
+    Ts[row + col * lds] = (row <= col + 1) ? H[(kw + row) + (size_t)(kw + col) * ldh] : mk(0.0, 0.0);
+    Zs[row + col * lds] = mk(row == col ? 1.0 : 0.0, 0.0);
+  }
+  cta_sync();
+  // Schur factorisation with the deflation test taken as the eigenvalues converge (AedStop): on return ns is the
+  // undeflated count and the positions istop+1 .. jw-1 are triangular (the block 0 .. istop is still Hessenberg)
+  AedStop st; st.s1 = cabs1(s); st.smlnum = smlnum; st.nd_skip = (sh.nibble * sh.nw) / 100 + 1; st.want = nshift_want;
+  int ns = 0, istop = -1;
+  const int bad = smem_hqr<true>(g, Ts, lds, jw, jw, sh.sm, sh.ctl, sh.cur, sh.rec, &st, &ns, &istop);
+  HQR_PROF(13);
+  *nshift = 0;
+  if (bad) return 0;                  // the window did not reach Schur form (never seen): a plain sweep follows
+  const int nd = jw - ns;
+  // ---- shifts of the next sweep: the converged, undeflated eigenvalues (positions istop+1 .. ns-1)
+  const int navail = ns - 1 - istop;
+  if (navail >= 2) {
+    for (int b = c.tid; b < nshift_want; b += c.nt) { const int j = ns - 1 - (b % navail); sh.shifts[b] = Ts[j + j * lds]; }
+    *nshift = nshift_want;
+  }
+  if (nd == 0) { cta_sync(); HQR_PROF(10); return 0; }
+  if (sh.prof && c.tid == 0) sh.prof[12] += nd;
+  for (int j = ns + c.tid; j < jw; j += c.nt) w[kw + j] = Ts[j + j * lds];
+  if (ns == 0) {                      // the whole window deflated
+    if (c.tid == 0 && kw > L) H[kw + (size_t)(kw - 1) * ldh] = mk(0.0, 0.0);
+    cta_sync();
+    HQR_PROF(10);
+    return nd;
+  }
+  cta_sync();                         // shifts and eigenvalues are read before T changes
+  // ---- return of T(0:ns, 0:ns) + spike to Hessenberg form
+  if (ns > 1 && !is_zero(s)) {
+    cplx* v = sh.sm;
+    for (int i = c.tid; i < ns; i += c.nt) v[i] = conj(Zs[i * lds]);
+    cta_sync();
+    cplx beta = v[0];
+    cta_sync();
+    cplx tau = cta_zlarfg(c, ns, beta, v + 1);
+    cta_sync();
+    if (c.tid == 0) v[0] = mk(1.0, 0.0);
+    cta_sync();
+    if (!is_zero(tau)) aed_reflect(c, Zs, lds, jw, ns, 0, v, tau);
+    for (int j = 0; j + 2 < ns; ++j) {              // ZGEHD2: reflector from T(j+1:ns-1, j)
+      cplx* col = Ts + (size_t)j * lds;
+      cplx alpha = col[j + 1];
+      cta_sync();
+      tau = cta_zlarfg(c, ns - j - 1, alpha, col + j + 2);
+      cta_sync();
+      for (int i = 1 + c.tid; i < ns - j - 1; i += c.nt) { v[i] = col[j + 1 + i]; col[j + 1 + i] = mk(0.0, 0.0); }
+      if (c.tid == 0) { v[0] = mk(1.0, 0.0); col[j + 1] = alpha; }
+      cta_sync();
+      if (!is_zero(tau)) aed_reflect(c, Zs, lds, jw, ns, j + 1, v, tau);
+    }
+  }
+  HQR_PROF(14);
+  // ---- the reduced window back in place (with explicit zeros on the second subdiagonal, which window loads read)
+  if (c.tid == 0) {
+    if (kw > L) H[kw + (size_t)(kw - 1) * ldh] = s * conj(Zs[0]);
+    H[(kw + ns) + (size_t)(kw + ns - 1) * ldh] = mk(0.0, 0.0);
+  }
+  for (int q = c.tid; q < ns * ns; q += c.nt) {
+    const int col = q / ns, row = q - col * ns;
+    if (row <= col + 2) H[(kw + row) + (size_t)(kw + col) * ldh] = (row <= col + 1) ? Ts[row + col * lds] : mk(0.0, 0.0);
+  }
+  // ---- the block above the window: H(L:kw-1, kw:kw+ns-1) = H(L:kw-1, kw:I) Z(:, 0:ns-1)
+  if (jw <= 32) aed_slab<16>(c.tid, c.nt, H, ldh, L, kw, jw, ns, Zs, lds);
+  else aed_slab<23>(c.tid, c.nt, H, ldh, L, kw, jw, ns, Zs, lds);
+  cta_sync();
+  HQR_PROF(10);
+  return nd;
+}
+
 // Eigenvalues of the Hessenberg matrix H (entries below the first subdiagonal must be zero) on
 // [ilo, ihi]; entries outside are read off the diagonal.  Returns 0 or the number of unconverged
 // eigenvalues (LAPACK-style info > 0).
@@ -885,13 +1142,13 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
       if (m <= 40) {                           // small: one warp with warp-level barriers beats CTA barriers
         if (c.wid == 0) {
           Grp gw; gw.tid = c.lane; gw.nt = c.ws; gw.warp = true;
-          bad = smem_hqr(gw, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur, sh.rec);
+          bad = smem_hqr<false>(gw, sh.win, sh.ldw, m, 0, w + L, sh.ctl, sh.cur, sh.rec);
           if (c.lane == 0) sh.ctl->pad = bad;
         }
         cta_sync();
         bad = sh.ctl->pad;
       } else {
-        bad = smem_hqr(g, sh.win, sh.ldw, m, w + L, sh.ctl, sh.cur, sh.rec);
+        bad = smem_hqr<false>(g, sh.win, sh.ldw, m, 0, w + L, sh.ctl, sh.cur, sh.rec);
       }
       if (bad) info += bad;
       I = L - 1; stagn = 0;
@@ -905,7 +1162,25 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
     if (m < 4 * ns) ns = m / 4;
     if (ns < 2) ns = 2;
     stagn += 1;
-    if (stagn % 6 == 0) {
+    int have_shifts = 0;
+    if (sh.nw > 0 && stagn % 6 != 0) {
+      // aggressive early deflation on the trailing window; while it keeps deflating more than NIBBLE per cent of the
+      // window no sweep is spent (ZLAQR0's rule)
+      const int nd = aed(c, sh, H, ldh, L, I, sh.nw, smlnum, w, ns, &have_shifts);
+      HQR_PROF(15);
+      if (nd > 0) {
+        I -= nd; stagn = 0;
+        const int m2 = I - L + 1;
+        if (100 * nd > sh.nibble * sh.nw || m2 <= sh.W) continue;
+        int ns2 = sh.ns_max;
+        if (m2 < 4 * ns2) ns2 = m2 / 4;
+        if (ns2 < 2) ns2 = 2;
+        if (ns2 != ns) { ns = ns2; have_shifts = 0; }        // the chain shortens with the block: recompute the shifts
+      }
+    }
+    if (have_shifts) {
+      cta_sync();
+    } else if (stagn % 6 == 0) {
       // exceptional shifts (ZLAQR0 style): diagonal entry plus 0.75 |subdiagonal|
       for (int b = c.tid; b < ns; b += c.nt) {
         const int k = I - b;
@@ -922,7 +1197,7 @@ SD_DEV int cta_hqr(const Cta& c, const HqrSmem& sh, cplx* H, int n, int ldh, int
       cta_sync();
       if (c.wid == 0) {                        // a 16x16 problem: one warp, warp-level barriers
         Grp gw; gw.tid = c.lane; gw.nt = c.ws; gw.warp = true;
-        smem_hqr(gw, sh.sm, lds, ns, sh.shifts, sh.ctl, sh.cur, sh.rec);
+        smem_hqr<false>(gw, sh.sm, lds, ns, 0, sh.shifts, sh.ctl, sh.cur, sh.rec);
       }
       cta_sync();
     }

@@ -8,7 +8,7 @@
 
 namespace stab {
 
-struct HqrLaunch { int W, ns_max, steps_max; };
+struct HqrLaunch { int W, ns_max, steps_max; int nw, nibble; };   // nw: deflation window (0 = classic deflation only)
 size_t hqr_smem_bytes(const HqrLaunch& q);
 // stage 4: eigenvalues of nmat upper Hessenberg matrices (hqr.cuh); `threads` per CTA (256), one CTA per matrix
 cudaError_t launch_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q, long long* prof,

@@ -5,13 +5,19 @@
 
 namespace stab {
 
+// scratch `sm`: the trailing block of the classic shift computation; the eigenvalues / Householder vector of the deflation window
+static size_t hqr_sm_entries(const HqrLaunch& q) { size_t a = (size_t)q.ns_max * (q.ns_max + 1); return a > 64 ? a : 64; }
+
+// reflector record: a pass of the multishift chain, or a whole two-bulge QR iteration on a block that fits the window
+static size_t hqr_rec_entries(const HqrLaunch& q) { size_t a = (size_t)q.steps_max * q.ns_max, b = 2 * ((size_t)q.W + 2); return a > b ? a : b; }
+
 size_t hqr_smem_bytes(const HqrLaunch& q) {
   size_t b = 160 * sizeof(double);
   b += (size_t)q.W * (q.W + 1) * sizeof(cplx);
-  b += (size_t)q.steps_max * q.ns_max * sizeof(Rot);
+  b += hqr_rec_entries(q) * sizeof(Rot);
   b += (size_t)2 * q.ns_max * sizeof(Rot);
   b += (size_t)q.ns_max * sizeof(cplx);
-  b += (size_t)q.ns_max * (q.ns_max + 1) * sizeof(cplx);
+  b += hqr_sm_entries(q) * sizeof(cplx);
   b += sizeof(SmallCtl);
   return b;
 }
@@ -21,12 +27,12 @@ __global__ void __launch_bounds__(256, 2) k_hqr(cplx* Hq, size_t hstride, int n,
   unsigned char* sp = smem_raw;
   double* red = reinterpret_cast<double*>(sp); sp += 160 * sizeof(double);
   HqrSmem sh;
-  sh.W = q.W; sh.ldw = q.W + 1; sh.ns_max = q.ns_max; sh.steps_max = q.steps_max;
+  sh.W = q.W; sh.ldw = q.W + 1; sh.ns_max = q.ns_max; sh.steps_max = q.steps_max; sh.nw = q.nw; sh.nibble = q.nibble;
   sh.win = reinterpret_cast<cplx*>(sp); sp += (size_t)q.W * (q.W + 1) * sizeof(cplx);
-  sh.rec = reinterpret_cast<Rot*>(sp); sp += (size_t)q.steps_max * q.ns_max * sizeof(Rot);
+  sh.rec = reinterpret_cast<Rot*>(sp); { size_t a = (size_t)q.steps_max * q.ns_max, b = 2 * ((size_t)q.W + 2); sp += (a > b ? a : b) * sizeof(Rot); }
   sh.cur = reinterpret_cast<Rot*>(sp); sp += (size_t)2 * q.ns_max * sizeof(Rot);
   sh.shifts = reinterpret_cast<cplx*>(sp); sp += (size_t)q.ns_max * sizeof(cplx);
-  sh.sm = reinterpret_cast<cplx*>(sp); sp += (size_t)q.ns_max * (q.ns_max + 1) * sizeof(cplx);
+  sh.sm = reinterpret_cast<cplx*>(sp); { size_t a = (size_t)q.ns_max * (q.ns_max + 1); sp += (a > 64 ? a : 64) * sizeof(cplx); }
   sh.ctl = reinterpret_cast<SmallCtl*>(sp);
   Cta c = make_cta(red);
   const int p = blockIdx.x;

@@ -35,7 +35,7 @@ struct DevCtx { int device = 0; stabgpu_plan* cached = nullptr; StageRing ring; 
 std::vector<DevCtx> g_devs;
 int g_stage_threads = 4;      // host threads that copy one staged chunk into the caller's (pageable) array
 int g_pin_mode = 1;           // 1: pageable destinations go through the pinned staging ring; 0: plain cudaMemcpyAsync into them
-struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int hess_streams = 1; int evec_mode = 1; int lu_mode = 1; /* 1: blocked LU with DMMA updates, 0: v1 one-CTA kernel */ int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
+struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int qr_nw = 32, qr_nibble = 14; /* deflation window of the QR kernel (0: classic deflation only) and ZLAQR0's NIBBLE */ int hess_streams = 1; int evec_mode = 1; int lu_mode = 1; /* 1: blocked LU with DMMA updates, 0: v1 one-CTA kernel */ int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
 bool g_qrprof_on = false;
@@ -543,7 +543,8 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(pl->ev[ST_PREP + 1], s));
   {
-    HqrLaunch q; q.W = g_tune.W; q.ns_max = g_tune.ns; q.steps_max = g_tune.qr_steps;
+    HqrLaunch q; q.W = g_tune.W; q.ns_max = g_tune.ns; q.steps_max = g_tune.qr_steps; q.nw = g_tune.qr_nw; q.nibble = g_tune.qr_nibble;
+    if (q.nw >= q.W || q.nw > 45 || (2 * q.nw + 1) * q.nw > q.W * (q.W + 1)) q.nw = 0;     // the window must fit the shared-memory tile
     if (q.W - 2 < 2 * q.ns_max - 1 || q.steps_max < 2 * q.ns_max - 1 || q.W - 2 * q.ns_max - 1 < 4)
       return fail("libstabgpu: invalid QR tuning (window too small for the shift count)");
     long long* prof = nullptr;
@@ -707,6 +708,7 @@ int stabgpu_debug_qr_profile(int enable, long long* out16) {
 
 int stabgpu_set_hess_mode(int mode) { g_tune.hess_mode = mode; return 0; }
 int stabgpu_debug_set_qr_steps(int steps) { if (steps > 0) g_tune.qr_steps = steps; return 0; }
+int stabgpu_debug_set_qr_aed(int nw, int nibble) { if (nw >= 0) g_tune.qr_nw = nw; if (nibble >= 0) g_tune.qr_nibble = nibble; return 0; }
 int stabgpu_set_evec_mode(int mode) { g_tune.evec_mode = mode; return 0; }
 int stabgpu_set_lu_mode(int mode) { g_tune.lu_mode = mode; return 0; }
 

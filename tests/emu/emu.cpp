@@ -5,6 +5,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdlib>
+#include <algorithm>
 #include "../../stab_b200/csrc/common.cuh"
 #include "../../stab_b200/csrc/tables.cuh"
 #include "../../stab_b200/csrc/assemble.cuh"
@@ -35,13 +36,13 @@ int emu_hessenberg(cplx* A, int n, int ilo, int ihi, cplx* tau) {
 }
 
 // H must be upper Hessenberg with explicit zeros below the subdiagonal
-int emu_hqr(cplx* H, int n, int ilo, int ihi, cplx* w, int W, int ns_max, int steps_max) {
+int emu_hqr(cplx* H, int n, int ilo, int ihi, cplx* w, int W, int ns_max, int steps_max, int nw, int nibble) {
   std::vector<double> red(256);
   Cta c = make_cta(red.data());
   HqrSmem sh;
-  sh.W = W; sh.ldw = W + 1;
-  std::vector<cplx> win((size_t)W * (W + 1)), shifts(ns_max), sm((size_t)ns_max * (ns_max + 1));
-  std::vector<Rot> rec((size_t)steps_max * ns_max), cur(2 * ns_max);
+  sh.W = W; sh.ldw = W + 1; sh.nw = nw; sh.nibble = nibble;
+  std::vector<cplx> win((size_t)W * (W + 1)), shifts(ns_max), sm((size_t)ns_max * (ns_max + 1) > 64 ? (size_t)ns_max * (ns_max + 1) : 64);
+  std::vector<Rot> rec(std::max((size_t)steps_max * ns_max, 2 * ((size_t)W + 2))), cur(2 * ns_max);
   SmallCtl ctl;
   sh.win = win.data(); sh.rec = rec.data(); sh.steps_max = steps_max; sh.ns_max = ns_max;
   sh.cur = cur.data(); sh.shifts = shifts.data(); sh.sm = sm.data(); sh.ctl = &ctl; sh.prof = nullptr;

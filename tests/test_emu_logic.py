@@ -127,20 +127,21 @@ def test_hessenberg_is_unitary_similarity():
     assert np.abs(q @ H @ q.conj().T - A).max() < 1e-12 * np.abs(A).max() * 40
 
 
-def emu_hqr(H, ilo, ihi, W=24, ns=4, steps=16):
+def emu_hqr(H, ilo, ihi, W=24, ns=4, steps=16, nw=12, nibble=14):
     n = H.shape[0]
     Hc = np.ascontiguousarray(H.T)
     w = np.empty(n, dtype=np.complex128)
-    info = emu().emu_hqr(cptr(Hc), n, ilo, ihi, cptr(w), W, ns, steps)
+    info = emu().emu_hqr(cptr(Hc), n, ilo, ihi, cptr(w), W, ns, steps, nw, nibble)
     return w, info
 
 
-@pytest.mark.parametrize("n,W,ns,steps", [(12, 24, 4, 16), (50, 24, 4, 16), (90, 32, 6, 20), (70, 20, 3, 7),
-                                          (150, 48, 16, 40), (260, 96, 16, 64), (100, 40, 16, 31)])
-def test_hqr_eigenvalues(n, W, ns, steps):
+@pytest.mark.parametrize("n,W,ns,steps,nw", [(12, 24, 4, 16, 12), (50, 24, 4, 16, 12), (90, 32, 6, 20, 16), (70, 20, 3, 7, 10),
+                                             (150, 48, 16, 40, 24), (260, 96, 16, 64, 44), (100, 40, 16, 31, 20),
+                                             (150, 48, 16, 40, 0), (180, 64, 16, 32, 32), (180, 64, 16, 32, 33), (220, 64, 16, 32, 45)])
+def test_hqr_eigenvalues(n, W, ns, steps, nw):
     A = _rand(n, 3 + n)
     H = np.triu(A, -1)
-    w, info = emu_hqr(H, 0, n - 1, W, ns, steps)
+    w, info = emu_hqr(H, 0, n - 1, W, ns, steps, nw)
     assert info == 0
     ref = np.linalg.eigvals(H)
     _, d = match_spectra(ref, w)
