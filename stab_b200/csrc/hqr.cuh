@@ -285,11 +285,18 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
   grp_sync(g);
   const int nbt = (g.nt >= 64) ? 32 : 0;                    // threads reserved for the bulge jobs (first warp)
   const int ntile = ns * (ns - 1) / 2;
+  const float inv_ns = 1.0f / (float)ns;                    // run-time shift count: no integer division per tile job
   int jj0 = (g.tid - nbt) - (ntile % (g.nt - nbt)); if (jj0 < 0) jj0 += g.nt - nbt;   // first line job of this thread (loop invariant)
 #ifdef STAB_CHASE_MB
   long long mb_t0_ = clock64();
 #endif
+#ifdef STAB_TL
+#define TL(w, k) do { if (threadIdx.x == (w) * 32 && g_tl_n[w] < 4000) { g_tl[w][g_tl_n[w]++] = (unsigned)clock() | 0u; g_tl_k[w][g_tl_n[w] - 1] = (k); } } while (0)
+#else
+#define TL(w, k)
+#endif
   for (int t = ta; t < tb; ++t) {
+    TL(0, 0); TL(1, 0);
     const Rot* cb = cur + (t & 1) * ns;
     Rot* nb = cur + ((t + 1) & 1) * ns;
     const bool more = (t + 1 < tb);
@@ -330,6 +337,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
       }
     }
 #endif
+    TL(0, 1);
     // ---- tile and line jobs -----------------------------------------------------------------
     if (blo <= bhi && (nbt == 0 || g.tid >= nbt)) {
       const int klo = kb0 + t - 2 * blo;                     // position of the leading active bulge
@@ -342,7 +350,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
       const int w0 = g.tid - nbt, wn = g.nt - nbt;
 #ifndef STAB_MB_NOTILE
       for (int j = w0; j < ntile; j += wn) {
-        const int p = j / ns, i = j - p * ns;
+        const int p = NSC ? j / ns : (int)(((float)j + 0.5f) * inv_ns), i = j - p * ns;   // j < 2^10: exact
         int b, bp;
         if (i <= p) { b = p + 1; bp = i; } else { b = ns - 1 - p; bp = i - p - 1; }
         if (bp < blo || b > bhi) continue;
@@ -393,6 +401,7 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
 #ifdef STAB_CHASE_MB
     if ((g.tid & 31) == 0) { long long now_ = clock64(); g_chase_busy[g.tid >> 5] += now_ - mb_t0_; }
 #endif
+    TL(1, 1);
     grp_sync(g);
 #ifdef STAB_CHASE_MB
     mb_t0_ = clock64();
