@@ -68,15 +68,20 @@ SD_DEV void cta_bal_reduce(const Cta& c, double& cs, double& rs, double& cam, in
 // cnt: int workspace of n entries (global or shared).  Returns ilo/ihi through pointers
 // (every thread gets the same values).
 // wsp: double workspace of balance_wsp_doubles(n, bal_b) entries (shared memory on the device).
-SD_HD size_t balance_wsp_doubles(int n, int bal_b) { return (size_t)2 * n + (size_t)2 * bal_b * n + 2; }
+SD_HD size_t balance_wsp_doubles(int n, int bal_b) { return (size_t)2 * n + (size_t)2 * bal_b * n + 2 + 4 * (size_t)bal_b; }
 SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, int* cnt, double* wsp, int bal_b, int& ilo_out, int& ihi_out) {
   int k = 0;      // first active index
   int l = n;      // one past last active index
   // ---- row isolation: push rows with zero off-diagonal part (within columns [0,l)) down ----
-  for (int r = c.tid; r < n; r += c.nt) {
+  for (int r = c.tid; r < n; r += c.nt) {       // eight loads in flight per thread: the scan is latency bound
     int m = 0;
-    for (int j = 0; j < n; ++j)
-      if (j != r && !is_zero(A[r + (size_t)j * lda])) ++m;
+    for (int j0 = 0; j0 < n; j0 += 8) {
+      cplx v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (j0 + u < n) ? A[r + (size_t)(j0 + u) * lda] : mk(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (j0 + u != r && !is_zero(v[u])) ++m;
+    }
     cnt[r] = m;
   }
   cta_sync();
@@ -114,8 +119,13 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
   // ---- column isolation: push columns with zero off-diagonal part (rows [k,l)) left ----
   for (int j = c.tid; j < l; j += c.nt) {
     int m = 0;
-    for (int r = k; r < l; ++r)
-      if (r != j && !is_zero(A[r + (size_t)j * lda])) ++m;
+    for (int r0 = k; r0 < l; r0 += 8) {
+      cplx v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (r0 + u < l) ? A[(r0 + u) + (size_t)j * lda] : mk(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (r0 + u != j && !is_zero(v[u])) ++m;
+    }
     cnt[j] = m;
   }
   cta_sync();
@@ -161,6 +171,7 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
   double* cbuf = wsp + 2 * n;             // bal_b x n : |A(r, i_e)|^2
   double* rbuf = cbuf + (size_t)bal_b * n;   // bal_b x n : |A(i_e, j)|^2
   int* flag = reinterpret_cast<int*>(rbuf + (size_t)bal_b * n);
+  double* part = rbuf + (size_t)bal_b * n + 2;   // 4 x bal_b: partial sums / maxima of the block's indices
   int lb = 0; while ((1 << (lb + 1)) <= bal_b) ++lb;   // bal_b is a power of two
   const int B = 1 << lb;
   for (int i = c.tid; i < n; i += c.nt) { fs[i] = 1.0; fi[i] = 1.0; }
@@ -198,6 +209,49 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
         }
       }
       cta_sync();
+#ifndef STAB_EMU
+      {
+        // The staging loads of the NEXT block are pure latency (HBM round trips with nothing to overlap): pull its
+        // 128-byte lines into L2 now, under this block's decisions.  No registers, no shared memory.
+        const int i1 = (i0 + B < l) ? i0 + B : k;             // the first block of the next sweep after the last one
+        const int nb1 = (l - i1 < B) ? (l - i1) : B;
+        const int lines_c = (l * 16 + 127) >> 7;              // lines per column (rows 0..l-1)
+        for (int q = c.tid; q < nb1 * lines_c; q += c.nt) {
+          const int e = q / lines_c, ln = q - e * lines_c;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(A + (size_t)(i1 + e) * lda) + ((size_t)ln << 7)));
+        }
+        for (int j = k + c.tid; j < n; j += c.nt) {           // rows i1..i1+nb1-1 of column j: one or two lines
+          const char* q = reinterpret_cast<const char*>(A + i1 + (size_t)j * lda);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (nb1 - 1) * 16));
+        }
+      }
+#endif
+      // (a) every index of the block in parallel, one warp each: its sums and maxima over the rows / columns OUTSIDE the
+      //     block, whose factors cannot change while the block is decided
+      for (int e = c.wid; e < nb; e += c.nw) {
+        const double* cb = cbuf + (size_t)e * n;
+        const double* rb = rbuf + (size_t)e * n;
+        double cs = 0.0, rs = 0.0, cam = 0.0, ram = 0.0;
+        for (int r = c.lane; r < l; r += c.ws) {
+          if (r >= i0 && r < i0 + nb) continue;
+          const double w = fi[r];                           // row factors chosen so far (1 for r < k)
+          const double v = cb[r] * (w * w);
+          if (r >= k) cs += v;
+          cam = fmax(cam, v);
+        }
+        for (int j = k + c.lane; j < n; j += c.ws) {
+          if (j >= i0 && j < i0 + nb) continue;
+          const double w = fs[j];                           // column factors chosen so far (1 for j >= l)
+          const double v = rb[j] * (w * w);
+          if (j < l) rs += v;
+          ram = fmax(ram, v);
+        }
+        cs = warp_sum(cs); rs = warp_sum(rs); cam = warp_max(cam); ram = warp_max(ram);
+        if (c.lane == 0) { part[4 * e] = cs; part[4 * e + 1] = rs; part[4 * e + 2] = cam; part[4 * e + 3] = ram; }
+      }
+      cta_sync();
+      // (b) the decisions in order (Gauss-Seidel): only the nb in-block terms are weighted with the factors of the moment
       if (c.wid == 0) {
         for (int e = 0; e < nb; ++e) {
           const int i = i0 + e;
@@ -205,19 +259,17 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
           const double* rb = rbuf + (size_t)e * n;
           // column i: c = ||A(k:l, i)||_2, ca = max |A(0:l, i)| ; row i: r = ||A(i, k:l)||_2, ra = max |A(i, k:n)|
           double cs = 0.0, rs = 0.0, cam = 0.0, ram = 0.0;
-          for (int r = c.lane; r < l; r += c.ws) {
-            const double w = fi[r];                           // row factors chosen so far (1 for r < k)
-            const double v = cb[r] * (w * w);
-            if (r >= k) cs += v;
-            cam = fmax(cam, v);
-          }
-          for (int j = k + c.lane; j < n; j += c.ws) {
-            const double w = fs[j];                           // column factors chosen so far (1 for j >= l)
-            const double v = rb[j] * (w * w);
-            if (j < l) rs += v;
-            ram = fmax(ram, v);
+          for (int q = c.lane; q < nb; q += c.ws) {
+            const int r = i0 + q;                             // k <= r < l
+            double w = fi[r];
+            double v = cb[r] * (w * w);
+            cs += v; cam = fmax(cam, v);
+            w = fs[r];
+            v = rb[r] * (w * w);
+            rs += v; ram = fmax(ram, v);
           }
           cs = warp_sum(cs); rs = warp_sum(rs); cam = warp_max(cam); ram = warp_max(ram);
+          cs += part[4 * e]; rs += part[4 * e + 1]; cam = fmax(cam, part[4 * e + 2]); ram = fmax(ram, part[4 * e + 3]);
           const double sc = fs[i], isc = fi[i];
           cs *= sc * sc; cam *= sc * sc; rs *= isc * isc; ram *= isc * isc;   // this index's own factors (exact)
           double ca = sqrt(cam), ra = sqrt(ram);
