@@ -68,7 +68,10 @@ SD_DEV void cta_bal_reduce(const Cta& c, double& cs, double& rs, double& cam, in
 // cnt: int workspace of n entries (global or shared).  Returns ilo/ihi through pointers
 // (every thread gets the same values).
 // wsp: double workspace of balance_wsp_doubles(n, bal_b) entries (shared memory on the device).
-SD_HD size_t balance_wsp_doubles(int n, int bal_b) { return (size_t)2 * n + (size_t)2 * bal_b * n + 2 + 4 * (size_t)bal_b; }
+// row stride of the staged row block: n rounded up to 2 (mod 16) doubles, so that the bal_b rows a half warp stores at once
+// (index e fastest) fall into different shared-memory banks (stride n = 640 put all eight into ONE bank: 8-way replays)
+SD_HD int balance_rstride(int n) { return n + ((2 - (n & 15)) & 15); }
+SD_HD size_t balance_wsp_doubles(int n, int bal_b) { return (size_t)2 * n + (size_t)bal_b * n + (size_t)bal_b * balance_rstride(n) + 2 + 4 * (size_t)bal_b; }
 SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, int* cnt, double* wsp, int bal_b, int& ilo_out, int& ihi_out) {
   int k = 0;      // first active index
   int l = n;      // one past last active index
@@ -169,9 +172,10 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
   double* fs = wsp;                       // n: cumulative column factor (1 outside [k,l))
   double* fi = wsp + n;                   // n: its exact inverse (row factor)
   double* cbuf = wsp + 2 * n;             // bal_b x n : |A(r, i_e)|^2
-  double* rbuf = cbuf + (size_t)bal_b * n;   // bal_b x n : |A(i_e, j)|^2
-  int* flag = reinterpret_cast<int*>(rbuf + (size_t)bal_b * n);
-  double* part = rbuf + (size_t)bal_b * n + 2;   // 4 x bal_b: partial sums / maxima of the block's indices
+  double* rbuf = cbuf + (size_t)bal_b * n;   // bal_b x rst : |A(i_e, j)|^2
+  const int rst = balance_rstride(n);
+  int* flag = reinterpret_cast<int*>(rbuf + (size_t)bal_b * rst);
+  double* part = rbuf + (size_t)bal_b * rst + 2;   // 4 x bal_b: partial sums / maxima of the block's indices
   int lb = 0; while ((1 << (lb + 1)) <= bal_b) ++lb;   // bal_b is a power of two
   const int B = 1 << lb;
   for (int i = c.tid; i < n; i += c.nt) { fs[i] = 1.0; fi[i] = 1.0; }
@@ -205,7 +209,7 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int q = q0 + u * c.nt, e = q & (B - 1), j = k + (q >> lb);
-          if (q < totr && e < nb) rbuf[(size_t)e * n + j] = v[u];
+          if (q < totr && e < nb) rbuf[(size_t)e * rst + j] = v[u];
         }
       }
       cta_sync();
@@ -231,7 +235,7 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
       //     block, whose factors cannot change while the block is decided
       for (int e = c.wid; e < nb; e += c.nw) {
         const double* cb = cbuf + (size_t)e * n;
-        const double* rb = rbuf + (size_t)e * n;
+        const double* rb = rbuf + (size_t)e * rst;
         double cs = 0.0, rs = 0.0, cam = 0.0, ram = 0.0;
         for (int r = c.lane; r < l; r += c.ws) {
           if (r >= i0 && r < i0 + nb) continue;
@@ -256,7 +260,7 @@ SD_DEV void cta_balance(const Cta& c, cplx* A, int n, int lda, double* scale, in
         for (int e = 0; e < nb; ++e) {
           const int i = i0 + e;
           const double* cb = cbuf + (size_t)e * n;
-          const double* rb = rbuf + (size_t)e * n;
+          const double* rb = rbuf + (size_t)e * rst;
           // column i: c = ||A(k:l, i)||_2, ca = max |A(0:l, i)| ; row i: r = ||A(i, k:l)||_2, ra = max |A(i, k:n)|
           double cs = 0.0, rs = 0.0, cam = 0.0, ram = 0.0;
           for (int q = c.lane; q < nb; q += c.ws) {
