@@ -345,8 +345,8 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
       const int c0 = klo + 2;                                // first left-only column
       int nL = wsz - c0; if (nL < 0) nL = 0;
       const int nR = khi - rtop;                             // right-only rows rtop .. khi-1
-      const int nq = (ns + LINE_ROT - 1) / LINE_ROT;
-      const int nline = nL + nR;
+      constexpr int LR = (NSC == 1) ? 1 : ((NSC == 2) ? 2 : LINE_ROT);   // rotations per line job: no idle slots in the short chains of the small QR
+      const int nq = (ns + LR - 1) / LR;
       const int w0 = g.tid - nbt, wn = g.nt - nbt;
 #ifndef STAB_MB_NOTILE
       for (int j = w0; j < ntile; j += wn) {
@@ -381,10 +381,10 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
         cplx* base = iscol ? S + (c0 + v) * lds : S + (v + rtop);
         const int str = iscol ? 1 : lds;
         const double sgn = iscol ? 1.0 : -1.0;
-        cplx x1[LINE_ROT], x2[LINE_ROT]; Rot r[LINE_ROT]; bool on[LINE_ROT];
+        cplx x1[LR], x2[LR]; Rot r[LR]; bool on[LR];
 #pragma unroll
-        for (int e = 0; e < LINE_ROT; ++e) {
-          const int b = LINE_ROT * q + e;
+        for (int e = 0; e < LR; ++e) {
+          const int b = LR * q + e;
           on[e] = b >= blo && b <= bhi;
           const int k = kb0 + t - 2 * (on[e] ? b : blo);
           x1[e] = base[k * str]; x2[e] = base[(k + 1) * str];
@@ -392,10 +392,10 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
           r[e].s.im *= sgn;
         }
 #pragma unroll
-        for (int e = 0; e < LINE_ROT; ++e) apply_left(r[e], x1[e], x2[e]);
+        for (int e = 0; e < LR; ++e) apply_left(r[e], x1[e], x2[e]);
 #pragma unroll
-        for (int e = 0; e < LINE_ROT; ++e)
-          if (on[e]) { const int k = kb0 + t - 2 * (LINE_ROT * q + e); base[k * str] = x1[e]; base[(k + 1) * str] = x2[e]; }
+        for (int e = 0; e < LR; ++e)
+          if (on[e]) { const int k = kb0 + t - 2 * (LR * q + e); base[k * str] = x1[e]; base[(k + 1) * str] = x2[e]; }
       }
     }
 #ifdef STAB_CHASE_MB
@@ -577,8 +577,14 @@ SD_DEV int smem_hqr(const Grp& g, cplx* S, int lds, int m, int zrows, cplx* wout
 #ifdef STAB_MB_COUNT
     if (g.tid == 0 && blockIdx.x == 0) { g_steps[0] += 1; g_steps[1] += T; }
 #endif
-    if (WANTT) chase_tiles<0>(g, S, lds, 0, m, L, I, ctl->shift, nsh, 0, T, rec, cur, -zrows);
-    else chase_tiles<0>(g, S + L + (size_t)L * lds, lds, L, I - L + 1, L, I, ctl->shift, nsh, 0, T, rec, cur, 0);
+    // compile-time chain length: the index arithmetic folds and a line job carries exactly the chain's rotations
+    if (nsh == 2) {
+      if (WANTT) chase_tiles<2>(g, S, lds, 0, m, L, I, ctl->shift, nsh, 0, T, rec, cur, -zrows);
+      else chase_tiles<2>(g, S + L + (size_t)L * lds, lds, L, I - L + 1, L, I, ctl->shift, nsh, 0, T, rec, cur, 0);
+    } else {
+      if (WANTT) chase_tiles<1>(g, S, lds, 0, m, L, I, ctl->shift, nsh, 0, T, rec, cur, -zrows);
+      else chase_tiles<1>(g, S + L + (size_t)L * lds, lds, L, I - L + 1, L, I, ctl->shift, nsh, 0, T, rec, cur, 0);
+    }
   }
   if (ns_out) *ns_out = ns_und < 0 ? 0 : ns_und;
   if (istop_out) *istop_out = I;
