@@ -83,6 +83,24 @@ SD_HD cplx csqrt_(cplx z) {
   return mk(fabs(si), z.im >= 0.0 ? sr : -sr);
 }
 
+// Streaming load of one complex entry: no L1 allocation, evict-first in L2.  For operands that are read once per launch and
+// are far larger than the L2 (the trailing matrix of the Hessenberg GEMV: 1.9 GB per column step), so that the small
+// panels other kernels re-read every step (Y, V, T: ~200 MB) are not flushed out of the 126 MB L2 by the stream.
+#ifdef STAB_EMU
+SD_HD cplx ld_stream(const cplx* p) { return *p; }
+#else
+SD_DEV unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+SD_DEV cplx ld_stream(const cplx* p, unsigned long long pol) {
+  cplx v;
+  asm("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.re), "=d"(v.im) : "l"(p), "l"(pol));
+  return v;
+}
+#endif
+
 // machine constants as LAPACK's DLAMCH reports them
 #define SD_EPS   1.1102230246251565e-16      /* DLAMCH('E') = 2^-53 */
 #define SD_ULP   2.2204460492503131e-16      /* DLAMCH('P') = eps*base */

@@ -188,11 +188,21 @@ SD_DEV void cta_hb_gemv(const Cta& c, const HessBatch& hb, int mat, int panel, i
     cplx a0 = mk(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
     const cplx* ap = A + r;
     int cc = c0;
+#ifdef STAB_EMU
     for (; cc + 3 < c1; cc += 4) {
       const cplx x0 = ap[(size_t)cc * lda], x1 = ap[(size_t)(cc + 1) * lda], x2 = ap[(size_t)(cc + 2) * lda], x3 = ap[(size_t)(cc + 3) * lda];
       fma_acc(a0, x0, sv[cc - c0]); fma_acc(a1, x1, sv[cc + 1 - c0]); fma_acc(a2, x2, sv[cc + 2 - c0]); fma_acc(a3, x3, sv[cc + 3 - c0]);
     }
     for (; cc < c1; ++cc) fma_acc(a0, ap[(size_t)cc * lda], sv[cc - c0]);
+#else
+    const unsigned long long pol = l2_policy_evict_first();   // the trailing matrix streams through once: keep the panels in L2
+    for (; cc + 3 < c1; cc += 4) {
+      const cplx x0 = ld_stream(ap + (size_t)cc * lda, pol), x1 = ld_stream(ap + (size_t)(cc + 1) * lda, pol),
+                 x2 = ld_stream(ap + (size_t)(cc + 2) * lda, pol), x3 = ld_stream(ap + (size_t)(cc + 3) * lda, pol);
+      fma_acc(a0, x0, sv[cc - c0]); fma_acc(a1, x1, sv[cc + 1 - c0]); fma_acc(a2, x2, sv[cc + 2 - c0]); fma_acc(a3, x3, sv[cc + 3 - c0]);
+    }
+    for (; cc < c1; ++cc) fma_acc(a0, ld_stream(ap + (size_t)cc * lda, pol), sv[cc - c0]);
+#endif
     Yp[r] = (a0 + a1) + (a2 + a3);
   }
 }
