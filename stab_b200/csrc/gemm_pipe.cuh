@@ -92,35 +92,58 @@ SD_DEV void gemm_pipe_run(const ProbF& probf, int tiles_i, int tiles_j, int nmat
   };
   constexpr int NLD = (TM * GEMM_KC) / GEMM_THREADS, NRD = (TN * GEMM_KC) / GEMM_THREADS;
   static_assert(NLD + NRD <= GEMM_KC / 2 && G::NACC <= GEMM_KC / 2, "one load slice per k-step");
-  // one cp.async (16 B per thread) of the operand chunk of `it` into ring stage `stage`: slice u of NLD + NRD
-  auto issue_one = [&](const Item& it, int stage, int u) {
-    double* sL = smem + stage * G::STAGE;
-    double* sR = sL + GEMM_KC * G::SLD;
+  static_assert(GEMM_THREADS % (4 * TM) == 0 && GEMM_THREADS % (4 * TN) == 0 && (GEMM_THREADS / 4) % TM == 0 && (GEMM_THREADS / 4) % TN == 0,
+                "a thread's slices differ only in k");
+  // ---- operand loader.  Slice u of a thread copies element (i, l0 + u DL) of the L chunk (u < NLD) or (l0 + u DL, j) of the
+  // R chunk: i / j and l0 are per-thread constants and DL = 256 / TM (256 / TN) is a compile-time step, so everything that
+  // depends on the work item -- base pointers of the tile and chunk, bounds -- is computed ONCE per item (prep_ld, sliced
+  // into the k-loop of the previous item) and a slice is a pointer plus u steps, a compare and the cp.async.  (Round 1
+  // recomputed the 64-bit address arithmetic in every slice: 58 of the 76 instructions between two DMMA groups.)
+  constexpr int DLL = GEMM_THREADS / TM, DLR = GEMM_THREADS / TN;
+  const int iL = LKFAST ? (tid >> 2) % TM : tid % TM;
+  const int l0L = LKFAST ? (tid & 3) + 4 * (tid / (4 * TM)) : tid / TM;
+  const int jR = RKFAST ? (tid >> 2) % TN : tid % TN;
+  const int l0R = RKFAST ? (tid & 3) + 4 * (tid / (4 * TN)) : tid / TN;
+  const unsigned dstL0 = (unsigned)__cvta_generic_to_shared(smem + l0L * G::SLD + 2 * iL);                       // stage 0, slice 0
+  const unsigned dstR0 = (unsigned)__cvta_generic_to_shared(smem + GEMM_KC * G::SLD + l0R * G::SRD + 2 * jR);
+  struct Ld { const cplx* pL; const cplx* pR; long long sL, sR; int kL, kR; };     // kL / kR: k entries left from l0 (<= 0: none, also when the row / column is out of range)
+  auto prep_ld = [&](const Item& it, Ld& d) {
     const bool second = it.chunk >= it.nch1;
     const int k0 = (second ? it.chunk - it.nch1 : it.chunk) * GEMM_KC;
     const int Kc = second ? it.p.K2 : it.p.K;
     const cplx* Lb = second ? it.p.L2 : it.p.L;
     const cplx* Rb = second ? it.p.R2 : it.p.R;
+    d.kL = (it.i0 + iL < it.p.m) ? Kc - k0 - l0L : 0;
+    d.kR = (it.j0 + jR < it.p.nc) ? Kc - k0 - l0R : 0;
+    d.pL = Lb + (long long)(it.i0 + iL) * it.p.lsi + (long long)(k0 + l0L) * it.p.lsl;
+    d.pR = Rb + (long long)(k0 + l0R) * it.p.rsl + (long long)(it.j0 + jR) * it.p.rsj;
+    d.sL = DLL * it.p.lsl; d.sR = DLR * it.p.rsl;
+  };
+  auto issue_one = [&](const Ld& d, int stage, int u) {          // u is a compile-time constant at every call site
     if (u < NLD) {
-      const int idx = tid + u * GEMM_THREADS;
-      int i, l;
-      if (LKFAST) { l = (idx & 3) + 4 * (idx / (4 * TM)); i = (idx >> 2) % TM; } else { i = idx % TM; l = idx / TM; }
-      const bool ok = (it.i0 + i < it.p.m) && (k0 + l < Kc);
-      const cplx* src = ok ? Lb + (long long)(it.i0 + i) * it.p.lsi + (long long)(k0 + l) * it.p.lsl : Lb;
-      cp_async16_zfill(sL + l * G::SLD + 2 * i, src, ok);
+      const bool ok = u * DLL < d.kL;
+      const cplx* src = d.pL + (ok ? u * d.sL : 0);
+      const unsigned dst = dstL0 + (unsigned)((stage * G::STAGE + u * DLL * G::SLD) * sizeof(double));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0));
     } else {
-      const int idx = tid + (u - NLD) * GEMM_THREADS;
-      int j, l;
-      if (RKFAST) { l = (idx & 3) + 4 * (idx / (4 * TN)); j = (idx >> 2) % TN; } else { j = idx % TN; l = idx / TN; }
-      const bool ok = (it.j0 + j < it.p.nc) && (k0 + l < Kc);
-      const cplx* src = ok ? Rb + (long long)(k0 + l) * it.p.rsl + (long long)(it.j0 + j) * it.p.rsj : Rb;
-      cp_async16_zfill(sR + l * G::SRD + 2 * j, src, ok);
+      const int v = u - NLD;
+      const bool ok = v * DLR < d.kR;
+      const cplx* src = d.pR + (ok ? v * d.sR : 0);
+      const unsigned dst = dstR0 + (unsigned)((stage * G::STAGE + v * DLR * G::SRD) * sizeof(double));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0));
     }
   };
-  auto load_c_one = [&](const Item& it, cplx (&dst)[G::NACC], int q) {
+  // ---- the C tile of a thread: entry q = (mt, nt) sits at pC + nt 4 + mt 8 ldc
+  struct Cd { cplx* pC; long long ldc8; int rrem, crem; };
+  auto prep_c = [&](const Item& it, Cd& d) {
+    const int i = it.i0 + rowbase + tg, j = it.j0 + colbase + g;
+    d.pC = it.p.C + i + (long long)j * it.p.ldc;
+    d.ldc8 = 8LL * it.p.ldc;
+    d.rrem = it.p.m - i; d.crem = it.p.nc - j;
+  };
+  auto load_c_one = [&](const Cd& d, cplx (&dst)[G::NACC], int q) {
     const int mt = q / G::NT, nt = q - mt * G::NT;
-    const int i = it.i0 + rowbase + nt * 4 + tg, j = it.j0 + colbase + mt * 8 + g;
-    dst[q] = (i < it.p.m && j < it.p.nc) ? it.p.C[i + (size_t)j * it.p.ldc] : mk(0.0, 0.0);
+    dst[q] = (nt * 4 < d.rrem && mt * 8 < d.crem) ? d.pC[nt * 4 + mt * d.ldc8] : mk(0.0, 0.0);
   };
   // the sign of a thread's B fragment is a per-thread constant: flip the sign bit on the integer pipe
   // (a DADD would queue behind the DMMAs on the FP64 pipe)
@@ -129,17 +152,22 @@ SD_DEV void gemm_pipe_run(const ProbF& probf, int tiles_i, int tiles_j, int nmat
   Item cur; cur.t = blockIdx.x; load_tile(cur);
   if (!cur.valid) return;
   cplx acc[G::NACC], cpre[G::NACC];
+  Ld lnxt; Cd ccur, cnxt;
+  prep_c(cur, ccur);
 #pragma unroll
   for (int q = 0; q < G::NACC; ++q) cpre[q] = mk(0.0, 0.0);
   if (SUB) {
 #pragma unroll
-    for (int q = 0; q < G::NACC; ++q) load_c_one(cur, cpre, q);
+    for (int q = 0; q < G::NACC; ++q) load_c_one(ccur, cpre, q);
   }
+  prep_ld(cur, lnxt);
 #pragma unroll
-  for (int u = 0; u < NLD + NRD; ++u) issue_one(cur, 0, u);
+  for (int u = 0; u < NLD + NRD; ++u) issue_one(lnxt, 0, u);
   cp_async_commit_();
   Item nxt = cur; advance(nxt);
+  if (nxt.valid) { prep_ld(nxt, lnxt); prep_c(nxt, cnxt); } else { cnxt = ccur; }
   Item nn = nxt;
+  Ld lnn = lnxt; Cd cnn = cnxt;
   int stage = 0;
   while (cur.valid) {
     cp_async_wait_all_();
@@ -172,22 +200,22 @@ SD_DEV void gemm_pipe_run(const ProbF& probf, int tiles_i, int tiles_j, int nmat
       for (int mt = 0; mt < G::MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < G::NT; ++nt) dmma884(acc[mt * G::NT + nt].re, acc[mt * G::NT + nt].im, a[mt], b[nt]);
-      if (nxt.valid && ks < NLD + NRD) issue_one(nxt, stage ^ 1, ks);
-      if (pre_c && ks < G::NACC) load_c_one(nxt, cpre, ks);
+      if (nxt.valid && ks < NLD + NRD) issue_one(lnxt, stage ^ 1, ks);
+      if (pre_c && ks < G::NACC) load_c_one(cnxt, cpre, ks);
       if (ks == GEMM_KC / 2 - 3) { nn = nxt; if (nxt.valid) advance(nn); }
+      if (ks == GEMM_KC / 2 - 2) { if (nn.valid) prep_ld(nn, lnn); }
+      if (ks == GEMM_KC / 2 - 1) { if (nn.valid) prep_c(nn, cnn); }
     }
     cp_async_commit_();
     if (cur.chunk + 1 == cur.nchunks) {
 #pragma unroll
       for (int mt = 0; mt < G::MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < G::NT; ++nt) {
-          const int i = cur.i0 + rowbase + nt * 4 + tg, j = cur.j0 + colbase + mt * 8 + g;
-          if (i < cur.p.m && j < cur.p.nc) cur.p.C[i + (size_t)j * cur.p.ldc] = acc[mt * G::NT + nt];
-        }
+        for (int nt = 0; nt < G::NT; ++nt)
+          if (nt * 4 < ccur.rrem && mt * 8 < ccur.crem) ccur.pC[nt * 4 + mt * ccur.ldc8] = acc[mt * G::NT + nt];
     }
-    cur = nxt;
-    nxt = nn;
+    cur = nxt; ccur = cnxt;
+    nxt = nn; lnxt = lnn; cnxt = cnn;
     stage ^= 1;
   }
 }
