@@ -612,6 +612,15 @@ def main():
     roofline_gemm = {"kernel": "k_gemm_pipe<*> (persistent cp.async-pipelined DMMA GEMM: rank-32 updates and V^H A products of the Hessenberg stage)", "bound": "tensor", "achieved": gemm_tf, "peak": peak,
                      "unit": "TFLOP/s", "frac": gemm_tf / peak if peak else None, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
                      "traffic": (traffic or {}).get("k_gemm_pipe")}
+    # the largest single kernel after round 2: register-resident inverse iteration.  Algorithmic work per eigenvalue: the UL
+    # elimination carries the column and the right-hand side (2 complex FMAs per row below the pivot, sum_k 16 k = 8 n^2 flops)
+    invit_ms = evec_bd.get("invit", 0.0)
+    invit_flops = 8.0 * float(n) ** 3 * P
+    invit_tf = invit_flops / (invit_ms * 1e-3) / 1e12 if invit_ms > 0 else 0.0
+    roofline_invit = {"kernel": "k_invit<20> (largest single kernel: one warp per eigenvalue, Hessenberg columns staged by TMA bulk copies)",
+                      "bound": "fp64 vector (DFMA; 33.7 TFLOP/s measured on this pool in round 1, the DGEMM figure is used as the denominator)",
+                      "achieved": invit_tf, "peak": peak, "unit": "TFLOP/s", "frac": invit_tf / peak if peak else None,
+                      "flops_per_step": invit_flops, "ms_per_step": invit_ms}
     asm_ms = stage_ms.get("assemble", 0.0)
     asm_gbs = 16.0 * n * n * P / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0
     dominant = max(stage_ms, key=stage_ms.get)
@@ -631,8 +640,11 @@ def main():
         "roofline": roofline,
         "roofline_gemv": roofline_gemv,
         "roofline_gemm": roofline_gemm,
+        "roofline_invit": roofline_invit,
         "stages_ms_per_step": stage_ms,
         "dominant_stage": (dominant + " (shifted QR: latency / FP64-vector bound, no clean roofline -- time share only, SURVEY 8d)") if dominant == "qr" else dominant,
+        "qr": {"ms_per_step": stage_ms.get("qr", 0.0), "share_of_step": stage_ms.get("qr", 0.0) / total_stage,
+               "note": "shifted QR with aggressive early deflation: latency bound (profiles/r02_qr_cycles.txt, r02_ncu_hqr.txt: 100 MB DRAM per matrix), no clean roofline"},
         "hessenberg_breakdown_ms": hess_bd,
         "eigvec_breakdown_ms": evec_bd,
         "assembly_roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -387,7 +387,8 @@ SD_DEV void chase_tiles(const Grp& g, cplx* S, int lds, int g0, int wsz, int L, 
           const int b = LR * q + e;
           on[e] = b >= blo && b <= bhi;
           const int k = kb0 + t - 2 * (on[e] ? b : blo);
-          x1[e] = base[k * str]; x2[e] = base[(k + 1) * str];
+          x1[e] = mk(0.0, 0.0); x2[e] = mk(0.0, 0.0);
+          if (on[e]) { x1[e] = base[k * str]; x2[e] = base[(k + 1) * str]; }   // predicated loads: an idle slot must not read entries another job is writing
           r[e] = cb[on[e] ? b : blo];
           r[e].s.im *= sgn;
         }
