@@ -16,22 +16,31 @@ c = sb.read_deck(open(os.path.join(R, "tests", "golden", "ts_temporal_ny96.inp")
 c.params.ny = 128
 c.load_profile(os.path.join(R, "tests", "golden", "ts_profile.0"))
 print(f"# {ndev} x {torch.cuda.get_device_name(0)}; TS temporal alpha sweep, Ny=128 (n=640), eigenvectors on, {per} points per GPU per call")
-print("# one process, one stabgpu_temporal_batch call per line (pageable numpy destination arrays: the library's pinned staging ring)")
+print("# one process, one stabgpu_temporal_batch call per line; destination arrays pageable (numpy: the library's pinned staging ring + host copy threads)\n# or page-locked once with stabgpu_host_register (direct DMA)")
+base = np.linspace(0.05, 0.45, per, endpoint=False) + 0j
+n = 5 * c.params.ny
 ref = None
 for k in (1, 2, 4, 8):
     if k > ndev:
         break
     got = sb.init_multi(k)
     P = per * k
-    a = np.linspace(0.05, 0.45, P, endpoint=False) + 0j
-    sb.temporal_batch(c.params, c.vm, c.deta, c.d2eta, a, a * 0, want_vectors=True)          # warm-up: plans, rings
-    t0 = time.perf_counter()
-    omg, ev, info = sb.temporal_batch(c.params, c.vm, c.deta, c.d2eta, a, a * 0, want_vectors=True)
-    dt = time.perf_counter() - t0
-    same = ""
-    if k == 1:
-        ref = (omg.copy(), ev.copy())
-    else:
-        same = f"  first {per} points bit-identical to the 1-GPU call: {bool(np.array_equal(omg[:per], ref[0]) and np.array_equal(ev[:per], ref[1]))}"
-    print(f"devices {got}: {P} points in {dt * 1e3:.0f} ms = {P / dt:.0f} eigensolves/s, failed {int(np.count_nonzero(info))}{same}", flush=True)
-    del omg, ev
+    a = np.tile(base, k)                          # every shard solves the same `per` points: shard r must equal shard 0 bit for bit
+    for mode in ("pageable", "registered"):
+        omg = np.empty((P, n), dtype=np.complex128)
+        ev = np.empty((P, n, n), dtype=np.complex128)
+        info = np.zeros(P, dtype=np.int32)
+        if mode == "registered":
+            sb.host_register(ev); sb.host_register(omg)
+        sb.temporal_batch(c.params, c.vm, c.deta, c.d2eta, a, a * 0, want_vectors=True, out=(omg, ev, info))      # warm-up: plans, rings
+        t0 = time.perf_counter()
+        sb.temporal_batch(c.params, c.vm, c.deta, c.d2eta, a, a * 0, want_vectors=True, out=(omg, ev, info))
+        dt = time.perf_counter() - t0
+        if ref is None:
+            ref = (omg[:per].copy(), ev[:per].copy())
+        same = all(np.array_equal(omg[r * per:(r + 1) * per], ref[0]) and np.array_equal(ev[r * per:(r + 1) * per], ref[1]) for r in range(k))
+        print(f"devices {got}, {mode:10s} destination: {P} points in {dt * 1e3:.0f} ms = {P / dt:.0f} eigensolves/s, failed {int(np.count_nonzero(info))}, "
+              f"every shard bit-identical to the 1-GPU result: {bool(same)}", flush=True)
+        if mode == "registered":
+            sb.host_unregister(ev); sb.host_unregister(omg)
+        del omg, ev
