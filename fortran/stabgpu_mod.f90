@@ -36,6 +36,12 @@ module stabgpu_mod
        integer(c_size_t), value :: bytes
      end function stabgpu_host_register
 
+     !> deflation window of the QR stage (default 32; 0 = classic deflation only) and ZLAQR0's NIBBLE in per cent (default 14)
+     integer(c_int) function stabgpu_set_qr_deflation(window, nibble) bind(C, name='stabgpu_set_qr_deflation')
+       import :: c_int
+       integer(c_int), value :: window, nibble
+     end function stabgpu_set_qr_deflation
+
      integer(c_int) function stabgpu_host_unregister(ptr) bind(C, name='stabgpu_host_unregister')
        import :: c_int, c_ptr
        type(c_ptr), value :: ptr

@@ -67,6 +67,10 @@ const char* stabgpu_last_error(void);
 int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb);
 /* tuning knobs of the QR stage (window size, shifts per sweep, threads); 0 keeps the default */
 int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads);
+/* Aggressive early deflation of the QR stage (the ZLAQR3 step of the ZHSEQR inside the reference's ZGEEV): deflation window
+ * (default 32; 0 = classic ZLAHQR-style deflation only, the round-1 algorithm -- kept as a validation switch) and ZLAQR0's
+ * NIBBLE in per cent (default 14).  Negative values keep the current setting. */
+int stabgpu_set_qr_deflation(int window, int nibble);
 /* Hessenberg stage variant: 1 (default) batched blocked reduction with DMMA tensor-core updates; 2 the same with a
  * scalar-FMA GEMM (validation of the tensor-core path); 0 the unblocked one-CTA-per-matrix kernel of v1; 5 as 1 with the right and
  * left trailing updates fused into one rank-64 pass (measured slower, kept as a validated variant) */

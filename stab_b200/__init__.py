@@ -21,6 +21,7 @@ from .binding import (  # noqa: F401
     init_multi,
     device_count,
     set_host_staging,
+    set_qr_deflation,
     host_register,
     host_unregister,
     finalize,

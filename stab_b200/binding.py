@@ -78,6 +78,7 @@ def lib():
     proto("stabgpu_last_error", cp, [])
     proto("stabgpu_device_info", i, [cp, i, _ip, _dp])
     proto("stabgpu_set_tuning", i, [i, i, i, i])
+    proto("stabgpu_set_qr_deflation", i, [i, i])
     proto("stabgpu_set_hess_mode", i, [i])
     proto("stabgpu_set_evec_mode", i, [i])
     proto("stabgpu_set_lu_mode", i, [i])
@@ -253,6 +254,11 @@ def init_multi(max_devices: int = 0) -> int:
 
 def device_count() -> int:
     return int(lib().stabgpu_device_count())
+
+
+def set_qr_deflation(window: int = -1, nibble: int = -1):
+    """stabgpu_set_qr_deflation: deflation window of the QR stage (0 = classic deflation only) and NIBBLE in per cent."""
+    _check(lib().stabgpu_set_qr_deflation(int(window), int(nibble)), "stabgpu_set_qr_deflation")
 
 
 def set_host_staging(pin_mode: int = -1, copy_threads: int = 0):

@@ -709,6 +709,7 @@ int stabgpu_debug_qr_profile(int enable, long long* out16) {
 int stabgpu_set_hess_mode(int mode) { g_tune.hess_mode = mode; return 0; }
 int stabgpu_debug_set_qr_steps(int steps) { if (steps > 0) g_tune.qr_steps = steps; return 0; }
 int stabgpu_debug_set_qr_aed(int nw, int nibble) { if (nw >= 0) g_tune.qr_nw = nw; if (nibble >= 0) g_tune.qr_nibble = nibble; return 0; }
+int stabgpu_set_qr_deflation(int window, int nibble) { return stabgpu_debug_set_qr_aed(window, nibble); }
 int stabgpu_set_evec_mode(int mode) { g_tune.evec_mode = mode; return 0; }
 int stabgpu_set_lu_mode(int mode) { g_tune.lu_mode = mode; return 0; }
 

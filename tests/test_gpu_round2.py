@@ -235,3 +235,28 @@ def test_sweep_enumerators_refuse_degenerate_increments():
         sb.mtemporal_points(0.1, 0.5, 0.1, 0.0, 1.0, 0.0)
     a, b = sb.mtemporal_points(0.1, 0.5, 0.1, 0.0, 0.0, 1.0)
     assert a.size == 4
+
+
+def test_qr_early_deflation_against_classic_deflation():
+    """The QR stage with aggressive early deflation (default) and with classic deflation only (the round-1 algorithm, kept as
+    a validation switch) on the same Ny = 64 TS operators: both pass the per-mode parity gate against the oracle, and their
+    spectra agree with each other as closely as either agrees with LAPACK.  Also the fortran/ binding's header entry."""
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=64)
+    al = np.array([0.12, 0.25, 0.38]) + 0j
+    got = {}
+    try:
+        for nw in (32, 0, 24):
+            sb.set_qr_deflation(nw, 14)
+            omg, _, info = sb.temporal_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], al, al * 0, want_vectors=False)
+            assert np.all(info == 0)
+            got[nw] = omg
+    finally:
+        sb.set_qr_deflation(32, 14)
+    for k in range(al.size):
+        p.alpha = complex(al[k])
+        r = so.solve_temporal(p, g["vm"], g["deta"], g["d2eta"], want_vectors=False)
+        for nw in got:
+            spectrum_parity(r["M"], r["omg"], got[nw][k], rel_tol=1e-10)
+        phys = np.abs(got[0][k]) < 2.0
+        _, d = match_spectra(got[0][k], got[32][k])
+        assert (d[phys] / np.maximum(np.abs(got[0][k][phys]), 1e-3)).max() < 1e-9
