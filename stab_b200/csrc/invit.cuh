@@ -23,6 +23,7 @@ namespace stab {
 
 constexpr int INVIT_WARPS = 8;
 constexpr int INVIT_CB = 8;        // columns per staged block
+constexpr int INVIT_PAD = 512;     // the branch-free boundary update reads a full 32-row slot: up to 31 entries past a column's end
 
 SD_DEV void cp_async16(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -143,8 +144,184 @@ struct InvitSlot<NS, -1> {
   SD_DEV static void run(int, int, bool, int, const cplx*, cplx*, cplx, double, cplx (&)[NS], cplx (&)[NS], unsigned&, cplx&, cplx&, int&, Prefetch&) {}
 };
 
-// grid: (ceil(n / (8*rounds)), batch), block 256.  smem: 2 * INVIT_CB * n complex + INVIT_WARPS * n bytes.  n <= 32 NS.
+
+// ---------------------------------------------------------------------------------------------------------------
+// Round 2, panel / bulk form of the same elimination (k_invit<NS, 1>, the default).  The per-step kernel above issues,
+// for every step, the pivot chain (compare, reciprocal, two complex products, boundary update, shuffle: ~200 dependent
+// cycles and a lane-divergent boundary branch) and then that step's bulk FMAs; with 8 warps per SM (the carried column
+// and the right-hand side fill the register file) nothing hides the chain: FP64 pipe 24 % busy.  Here the 8 steps of a
+// staged block are split:
+//   panel : the 8 pivot decisions and the update of the BOUNDARY slot only (rows 32 SB .. k-1, branch-free: every lane
+//           computes the update, selects keep the finished rows), recording (mq, yk) per step in shared memory and the
+//           interchange bits in a register;
+//   bulk  : the 8 recorded steps applied to the slots above the boundary -- one shared-memory load and 8 DFMAs per slot
+//           and step, no dependence on the pivot chain, warp-uniform branch on the interchange bit.
+// The pivot chain of a step depends only on the boundary slot, which the panel keeps current, so the bulk of a block may
+// trail its panel; at a slot edge (k = 32 SB: row k-1 is lane 31 of slot SB-1) the trailing steps are first applied to
+// slot SB-1 alone, then the edge step runs on that slot.  Every entry sees the same operations in the same order as in
+// the per-step kernel.
+struct InvitRec { cplx mq, yk; };
+
+// 1/d for d > 0 in the normal range: the 2^-23 seed of MUFU.RCP64H and one cubically convergent correction x (1 + e + e^2),
+// e = 1 - d x: relative error ~2^-69 before rounding -- three dependent FMAs instead of the five (and the range check with
+// its slow-path call) of the correctly rounded __drcp_rn.  The reciprocal sits on the pivot chain of every step.
+SD_DEV double rcp_fast(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  const double e = fma(-d, x, 1.0);
+  const double e2 = fma(e, e, e);
+  return fma(x, e2, x);
+}
+
+// pivot decision of the panel: as invit_pivot, with the dependent chain shortened -- the zero test comes from the CABS1
+// values the comparison already has, and the numerators are multiplied by conj(piv) beside the reciprocal of |piv|^2
+// instead of after it
+SD_DEV void invit_pivot_pb(cplx ak, cplx cdiag, cplx ydiag, double eps3, bool& sw, cplx& mq, cplx& yk) {
+  const double ca = cabs1(ak), cc = cabs1(cdiag);
+  sw = ca > cc;
+  const bool zero = !sw && cc == 0.0;                    // the chosen pivot is zero only if both candidates are
+  cplx piv = sw ? ak : cdiag;
+  if (zero) piv = mk(eps3, 0.0);
+  const cplx num = sw ? cdiag : ak;
+  const double rd = rcp_fast(fma(piv.re, piv.re, piv.im * piv.im));
+  const cplx tm = mulc(num, piv), ty = mulc(ydiag, piv);
+  mq = tm * rd;
+  yk = ty * rd;
+}
+
+// one panel step k (k & 31 != 0) of slot group SB: pivot, boundary slot SB, next carried diagonal
+template <int NS, int SB>
+SD_DEV void invit_panel_step(int k, int lane, cplx ak, cplx a, cplx lm, double eps3, cplx (&c)[NS], cplx (&y)[NS], unsigned& flags,
+                             cplx& cdiag, cplx& ydiag, bool& sw, cplx& mq, cplx& yk) {
+  const int kk = k & 31;
+  invit_pivot_pb(ak, cdiag, ydiag, eps3, sw, mq, yk);
+  if (lane == kk - 1) a -= lm;
+  const cplx cr = c[SB], yr = y[SB];
+  const cplx q = sw ? a : cr, p = sw ? cr : a;
+  cplx cn = p, yn = yr;
+  fms_acc(cn, mq, q);
+  fms_acc(yn, yk, q);
+  const bool below = lane < kk, at = lane == kk;
+  c[SB] = below ? cn : (at ? mq : cr);
+  y[SB] = below ? yn : (at ? yk : yr);
+  if (at && sw) flags |= (1u << SB);
+  cdiag = shfl_c(cn, kk - 1);
+  ydiag = shfl_c(yn, kk - 1);
+}
+
+// the edge step k = 32 SB (SB >= 1): all of slot SB-1 is above the pivot row, lane 0 of slot SB takes the multiplier
+template <int NS, int SB>
+SD_DEV void invit_panel_edge(int lane, cplx ak, cplx a, cplx lm, double eps3, cplx (&c)[NS], cplx (&y)[NS], unsigned& flags,
+                             cplx& cdiag, cplx& ydiag, bool& sw, cplx& mq, cplx& yk) {
+  constexpr int S1 = SB > 0 ? SB - 1 : 0;
+  invit_pivot_pb(ak, cdiag, ydiag, eps3, sw, mq, yk);
+  if (lane == 31) a -= lm;
+  const cplx cr = c[S1], yr = y[S1];
+  const cplx q = sw ? a : cr, p = sw ? cr : a;
+  cplx cn = p, yn = yr;
+  fms_acc(cn, mq, q);
+  fms_acc(yn, yk, q);
+  c[S1] = cn; y[S1] = yn;
+  if (lane == 0) {
+    c[SB] = mq; y[SB] = yk;
+    if (sw) flags |= (1u << SB);
+  }
+  cdiag = shfl_c(cn, 31);
+  ydiag = shfl_c(yn, 31);
+}
+
+// one recorded step applied to slots S0 .. S1-1 (all rows above the boundary)
+template <int NS, int S0, int S1>
+SD_DEV void invit_bulk_step(int lane, const cplx* __restrict__ acol, bool sw, cplx mq, cplx yk, cplx (&c)[NS], cplx (&y)[NS]) {
+  if (sw) {
+#pragma unroll
+    for (int s = S0; s < S1; ++s) {
+      const cplx a = acol[32 * s + lane];
+      fms_acc(y[s], yk, a); fms_acc(c[s], mq, a);
+    }
+  } else {
+#pragma unroll
+    for (int s = S0; s < S1; ++s) {
+      cplx a = acol[32 * s + lane];
+      const cplx cr = c[s];
+      fms_acc(y[s], yk, cr); fms_acc(a, mq, cr);
+      c[s] = a;
+    }
+  }
+}
+
+template <int NS, int SB>
+struct InvitGroup {
+  template <class Prefetch>
+  SD_DEV static void run(int n, int m, bool live, int lane, cplx* sH, InvitRec* rec, cplx lm, double eps3,
+                         cplx (&c)[NS], cplx (&y)[NS], unsigned& flags, cplx& cdiag, cplx& ydiag, int& buf, Prefetch& prefetch) {
+    constexpr int S1 = SB > 0 ? SB - 1 : 0;
+#pragma unroll 1
+    for (int bq = 3; bq >= 0; --bq) {
+      const int B = 4 * SB + bq;
+      if (8 * B > n - 1) continue;                       // block above the matrix (uniform)
+      prefetch.wait(buf);                                // block B landed (transaction barrier of its buffer)
+      __syncthreads();                                   // everyone left block B+1
+      if (B > 0) prefetch(B - 1, buf ^ 1);
+      const cplx* tile = sH + (size_t)buf * INVIT_CB * n;
+      const int k0 = 8 * B;
+      const int qhi = live ? min(INVIT_CB - 1, m - 1 - k0) : -1;   // steps k0+qhi .. k0+qlo of this block are this eigenvalue's
+      const bool edge = SB > 0 && bq == 0;               // q = 0 is the slot-edge step k = 32 SB
+      const int qlo = (B == 0 || edge) ? 1 : 0;          // k = 0 is no step; the edge step runs apart
+      unsigned swm = 0u;
+      // ---- panel ----
+      if (qhi >= qlo) {
+        cplx ak = tile[(size_t)qhi * n + k0 + qhi], a = tile[(size_t)qhi * n + 32 * SB + lane];
+#pragma unroll 1
+        for (int q = qhi; q >= qlo; --q) {
+          const int k = k0 + q;
+          const int qn = q > qlo ? q - 1 : q;            // next step's entries: loaded ahead of this step's pivot chain
+          const cplx ak_n = tile[(size_t)qn * n + k0 + qn], a_n = tile[(size_t)qn * n + 32 * SB + lane];
+          bool sw; cplx mq, yk;
+          invit_panel_step<NS, SB>(k, lane, ak, a, lm, eps3, c, y, flags, cdiag, ydiag, sw, mq, yk);
+          if (sw) swm |= 1u << q;
+          if (lane == 0) { rec[q].mq = mq; rec[q].yk = yk; }
+          ak = ak_n; a = a_n;
+        }
+      }
+      __syncwarp();
+      // ---- bulk ----
+      if (edge) {
+        if (qhi >= 0) {
+#pragma unroll 1
+          for (int q = qhi; q >= 1; --q)                 // bring slot SB-1 up to date, then the edge step on it
+            invit_bulk_step<NS, S1, SB>(lane, tile + (size_t)q * n, (swm >> q) & 1u, rec[q].mq, rec[q].yk, c, y);
+          {
+            bool sw; cplx mq, yk;
+            invit_panel_edge<NS, SB>(lane, tile[k0], tile[32 * S1 + lane], lm, eps3, c, y, flags, cdiag, ydiag, sw, mq, yk);
+            if (sw) swm |= 1u;
+            if (lane == 0) { rec[0].mq = mq; rec[0].yk = yk; }
+          }
+          __syncwarp();
+#pragma unroll 1
+          for (int q = qhi; q >= 0; --q)
+            invit_bulk_step<NS, 0, S1>(lane, tile + (size_t)q * n, (swm >> q) & 1u, rec[q].mq, rec[q].yk, c, y);
+        }
+      } else {
+#pragma unroll 1
+        for (int q = qhi; q >= qlo; --q)
+          invit_bulk_step<NS, 0, SB>(lane, tile + (size_t)q * n, (swm >> q) & 1u, rec[q].mq, rec[q].yk, c, y);
+      }
+      __syncwarp();                                      // records read before the next block's panel rewrites them
+      buf ^= 1;
+    }
+    InvitGroup<NS, SB - 1>::run(n, m, live, lane, sH, rec, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+  }
+};
 template <int NS>
+struct InvitGroup<NS, -1> {
+  template <class Prefetch>
+  SD_DEV static void run(int, int, bool, int, cplx*, InvitRec*, cplx, double, cplx (&)[NS], cplx (&)[NS], unsigned&, cplx&, cplx&, int&, Prefetch&) {}
+};
+
+// grid: (ceil(n / (8*rounds)), batch), block 256.  smem: 2 * INVIT_CB * n complex + INVIT_WARPS * n bytes (+ INVIT_PAD).  n <= 32 NS.
+// PB = 1: panel / bulk form (default), PB = 0: the per-step form (validation switch evec_mode 3).
+template <int NS, int PB>
 __global__ void __launch_bounds__(INVIT_WARPS * 32, 1)
 k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restrict__ lam, const int* __restrict__ kr,
         const double* __restrict__ hnorm, cplx* __restrict__ Y, size_t ystride, int* __restrict__ bad, int rounds) {
@@ -157,6 +334,7 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
   const double eps3 = fmax(SD_ULP * hnorm[p], smlnum);
   const double growto = 0.1 / sqrt((double)n);
   __shared__ uint64_t bars[2];                              // transaction barriers of the two staging buffers
+  __shared__ InvitRec recs[PB ? INVIT_WARPS * INVIT_CB : 1];  // (mq, yk) of the current block's steps, per warp
   if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   __syncthreads();
   unsigned par = 0u;                                        // phase parity of the two barriers (bits 0, 1), tracked by every thread
@@ -214,7 +392,8 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
     __syncthreads();                                        // previous round finished with both buffers
     int buf = 0;
     prefetch((n - 1) >> 3, 0);
-    InvitSlot<NS, NS - 1>::run(n, m, live, lane, H, sH, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+    if constexpr (PB != 0) InvitGroup<NS, NS - 1>::run(n, m, live, lane, sH, recs + wid * INVIT_CB, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+    else InvitSlot<NS, NS - 1>::run(n, m, live, lane, H, sH, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
     // ---- k = 0, then x = T_{m-1} ... T_1 y: a first-order recurrence in k.  The warp parks y, the multipliers and
     // the interchange flags in the (now idle) staging buffers and ONE lane runs the recurrence from shared memory
     // (~25 dependent cycles per row) instead of three warp shuffles per row ----

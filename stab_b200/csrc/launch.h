@@ -14,8 +14,9 @@ size_t hqr_smem_bytes(const HqrLaunch& q);
 cudaError_t launch_hqr(cplx* Hq, size_t hstride, int n, const int* ilohi, cplx* w, int* info, HqrLaunch q, long long* prof,
                        const double* hnorm, int nmat, int threads, cudaStream_t s);
 // stage 6: right eigenvectors of the Hessenberg matrices by register-resident inverse iteration (invit.cuh), n <= 1280;
-// picks the one-warp (n <= 640) or two-warp kernel and its register-slot count from n
+// picks the one-warp (n <= 640) or two-warp kernel and its register-slot count from n; per_step != 0 selects the per-step
+// form of the one-warp kernel (validation switch) instead of the panel / bulk form
 cudaError_t launch_invit(const cplx* Hh, size_t hstride, int n, const cplx* lam, const int* kr, const double* hnorm, cplx* Y,
-                         size_t ystride, int* bad, int rounds, int nmat, cudaStream_t s);
+                         size_t ystride, int* bad, int rounds, int nmat, int per_step, cudaStream_t s);
 
 }  // namespace stab

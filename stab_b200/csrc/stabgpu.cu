@@ -388,7 +388,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
   const size_t sm_old = warps * per_warp;
   if (sm_old > 227 * 1024) return fail("libstabgpu: matrix too large for the eigenvector kernel");
   CU(cudaFuncSetAttribute(k_evec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_old));
-  const bool fast = g_tune.evec_mode == 1 && g_tune.hess_mode != 0 && N <= 1280;
+  const bool fast = (g_tune.evec_mode == 1 || g_tune.evec_mode == 3) && g_tune.hess_mode != 0 && N <= 1280;   // 3: per-step inverse iteration (validation)
   const bool to_host = pl->evec_host != nullptr;
   const int nsub = !to_host ? 1 : (np >= 8 * 37 ? 8 : (np >= 4 * 37 ? 4 : (np >= 2 ? 2 : 1)));   // >= 37 matrices per sub-batch keep the kernels full
   pl->nsub = nsub;
@@ -410,7 +410,7 @@ int run_eigvecs(stabgpu_plan* pl, int scale_rows) {
     } else {
       const int rounds = 4;
       CU(launch_invit(pl->A.p + (size_t)m0 * st, st, N, pl->lam.p + (size_t)m0 * N, pl->kr.p + (size_t)m0 * N, pl->hnorm.p + m0,
-                      pl->V.p + (size_t)m0 * st, st, pl->vbad.p + (size_t)m0 * N, rounds, cnt, s));
+                      pl->V.p + (size_t)m0 * st, st, pl->vbad.p + (size_t)m0 * N, rounds, cnt, g_tune.evec_mode == 3, s));
       pl->launches += 1;
       // vectors the fast kernel rejected (no growth / overflow): ZLAEIN's retry vectors, v1 kernel, Hessenberg basis
       k_evec<<<grid_old, warps * 32, sm_old, s>>>(pl->A.p + (size_t)m0 * st, st, N, pl->ilohi.p + 2 * m0, pl->tau.p + (size_t)m0 * N,

@@ -260,3 +260,46 @@ def test_qr_early_deflation_against_classic_deflation():
         phys = np.abs(got[0][k]) < 2.0
         _, d = match_spectra(got[0][k], got[32][k])
         assert (d[phys] / np.maximum(np.abs(got[0][k][phys]), 1e-3)).max() < 1e-9
+
+
+@pytest.mark.parametrize("n,batch", [(40, 3), (97, 2), (200, 2), (417, 1), (640, 2)])
+def test_panel_bulk_inverse_iteration_against_per_step_form(n, batch):
+    """The panel / bulk form of the register-resident inverse iteration (default, k_invit<NS, 1>: pivot chain of a staged
+    8-column block first, recorded steps applied to the rows above afterwards) against the per-step form (evec_mode 3,
+    the round-1 kernel): every entry sees the same operations in the same order, only the reciprocal differs in its last
+    bits, so the vectors agree to rounding; residuals at the same level; on the Ny=64 TS operator (leading blocks kr < n
+    from ZGEBAL's isolated rows) as well."""
+    rng = np.random.default_rng(4000 + n)
+    A = (rng.standard_normal((batch, n, n)) + 1j * rng.standard_normal((batch, n, n))) / np.sqrt(n)
+    w1, V1, i1 = sb.zgeev_batch(A, want_vectors=True)
+    sb.set_evec_mode(3)
+    try:
+        w3, V3, i3 = sb.zgeev_batch(A, want_vectors=True)
+    finally:
+        sb.set_evec_mode(1)
+    assert np.all(i1 == 0) and np.all(i3 == 0)
+    assert np.array_equal(w1, w3)
+    assert np.abs(V1 - V3).max() < 1e-10
+    for b in range(batch):
+        r1 = eigpair_residuals(A[b], w1[b], V1[b]).max()
+        r3 = eigpair_residuals(A[b], w3[b], V3[b]).max()
+        assert r1 < max(1e-13, 4 * n * np.finfo(float).eps)
+        assert r1 < 4 * r3 + 1e-15
+
+
+def test_panel_bulk_inverse_iteration_on_the_ts_operator():
+    p, g = oracle_case("ts_temporal_ny96.inp", "ts_profile.0", ny=64)
+    al = np.array([0.12, 0.25, 0.38]) + 0j
+    omg1, ev1, info1 = sb.temporal_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], al, al * 0, want_vectors=True)
+    sb.set_evec_mode(3)
+    try:
+        omg3, ev3, info3 = sb.temporal_batch(to_params(p), g["vm"], g["deta"], g["d2eta"], al, al * 0, want_vectors=True)
+    finally:
+        sb.set_evec_mode(1)
+    assert np.all(info1 == 0) and np.all(info3 == 0)
+    assert np.array_equal(omg1, omg3)
+    # near-defective continuous-branch modes amplify the last-bit difference of the reciprocal; the discrete modes do not
+    phys = np.abs(omg1) < 2.0
+    d = np.abs(ev1 - ev3).max(axis=1)
+    assert d[phys].max() < 1e-8
+    assert np.median(d) < 1e-12
