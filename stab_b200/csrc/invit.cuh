@@ -319,6 +319,56 @@ struct InvitGroup<NS, -1> {
   SD_DEV static void run(int, int, bool, int, cplx*, InvitRec*, cplx, double, cplx (&)[NS], cplx (&)[NS], unsigned&, cplx&, cplx&, int&, Prefetch&) {}
 };
 
+
+// x = T_{m-1} ... T_1 y, the first-order recurrence that undoes the column operations:
+//   k = 1 .. m-1:  t = y_k - m_k prev;  interchanged ? (x_{k-1} = t, prev kept) : (x_{k-1} = prev, prev = t);   x_{m-1} = prev
+// as a warp-wide scan instead of one lane walking all rows (7 % of the kernel): a row acts on `prev` as the affine map
+// prev -> A prev + B with (A, B) = (1, 0) or (-m_k, y_k); lane l composes the maps of its chunk of R consecutive rows
+// (R odd: the chunks start in 8 different 16-byte bank groups, so the strided shared-memory reads are conflict free), five
+// shuffle steps give every lane the state entering its chunk, and a second pass over the chunk produces x.  A lane's first
+// store hits the last row its left neighbour still reads, so that one store waits for the warp.  |m_k| <= sqrt 2 (partial
+// pivoting), in practice the products decay; a product that overflows ends in a NaN vector, which the caller's growth test
+// hands to the retry kernel.
+SD_DEV void invit_recurrence_scan(int m, int lane, cplx* wy, const cplx* wc, const unsigned char* wf, cplx prev0) {
+  const int R = ((m - 1 + 31) / 32) | 1;
+  const int k0 = 1 + lane * R, k1 = min(k0 + R, m);
+  cplx A = mk(1.0, 0.0), B = mk(0.0, 0.0);
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    if (wf[k] == 0) {
+      const cplx mm = wc[k];
+      cplx nb = wy[k];
+      fms_acc(nb, mm, B);
+      B = nb;
+      A = -(mm * A);
+    }
+  }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const cplx Ae = mk(__shfl_up_sync(0xffffffffu, A.re, d), __shfl_up_sync(0xffffffffu, A.im, d));
+    const cplx Be = mk(__shfl_up_sync(0xffffffffu, B.re, d), __shfl_up_sync(0xffffffffu, B.im, d));
+    if (lane >= d) { fma_acc(B, A, Be); A = A * Ae; }
+  }
+  cplx Ax = mk(__shfl_up_sync(0xffffffffu, A.re, 1), __shfl_up_sync(0xffffffffu, A.im, 1));
+  cplx Bx = mk(__shfl_up_sync(0xffffffffu, B.re, 1), __shfl_up_sync(0xffffffffu, B.im, 1));
+  if (lane == 0) { Ax = mk(1.0, 0.0); Bx = mk(0.0, 0.0); }
+  cplx prev = Bx;
+  fma_acc(prev, Ax, prev0);                                 // the state entering this lane's chunk
+  cplx first = mk(0.0, 0.0);
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    cplx t = wy[k];
+    fms_acc(t, wc[k], prev);
+    const bool f = wf[k] != 0;
+    const cplx fin = f ? t : prev;
+    prev = f ? prev : t;
+    if (k == k0) first = fin; else wy[k - 1] = fin;
+  }
+  __syncwarp();                                             // the left neighbour has read its last row
+  if (k0 < k1) wy[k0 - 1] = first;
+  if (k1 == m && (k0 < k1 || (m == 1 && lane == 0))) wy[m - 1] = prev;   // the lane holding the last row (m = 1: no row at all)
+}
+
 // grid: (ceil(n / (8*rounds)), batch), block 256.  smem: 2 * INVIT_CB * n complex + INVIT_WARPS * n bytes (+ INVIT_PAD).  n <= 32 NS.
 // PB = 1: panel / bulk form (default), PB = 0: the per-step form (validation switch evec_mode 3).
 template <int NS, int PB>
@@ -335,7 +385,8 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
   const double growto = 0.1 / sqrt((double)n);
   __shared__ uint64_t bars[2];                              // transaction barriers of the two staging buffers
   __shared__ InvitRec recs[PB ? INVIT_WARPS * INVIT_CB : 1];  // (mq, yk) of the current block's steps, per warp
-  if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  constexpr unsigned NISS = PB ? INVIT_WARPS : 1;          // arrivals per staged block (panel / bulk form: one issuing lane per warp)
+  if (threadIdx.x == 0) { mbar_init(&bars[0], NISS); mbar_init(&bars[1], NISS); mbar_fence_init(); }
   __syncthreads();
   unsigned par = 0u;                                        // phase parity of the two barriers (bits 0, 1), tracked by every thread
 
@@ -357,6 +408,16 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
     struct Stager {
       const cplx* H; cplx* sH; uint64_t* bars; unsigned* parity; int n;
       __device__ void operator()(int B, int bufi) const {
+        if (PB != 0) {                                       // lane 0 of warp q issues column q: no warp carries the whole loop
+          if ((threadIdx.x & 31) != 0) return;
+          const int q = threadIdx.x >> 5, k = 8 * B + q;
+          const bool ok = k >= 1 && k <= n - 1;
+          const unsigned bytes = ok ? (unsigned)(k + 1) * 16u : 0u;
+          fence_async_smem();
+          mbar_arrive_expect_tx(bars + bufi, bytes);
+          if (ok) bulk_g2s(sH + ((size_t)bufi * INVIT_CB + q) * n, H + (size_t)(k - 1) * n, bytes, bars + bufi);
+          return;
+        }
         if (threadIdx.x != 0) return;
         cplx* dst = sH + (size_t)bufi * INVIT_CB * n;
         unsigned bytes = 0;
@@ -409,6 +470,11 @@ k_invit(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restri
         if (r < m) { wy[r] = y[s]; wc[r] = c[s]; wf[r] = (unsigned char)((flags >> s) & 1u); }
       }
       __syncwarp();
+      if constexpr (PB != 0) {
+        cplx piv = cdiag;
+        if (is_zero(piv)) piv = mk(eps3, 0.0);
+        invit_recurrence_scan(m, lane, wy, wc, wf, cdiv(ydiag, piv));
+      } else
       if (lane == 0) {
         cplx piv = cdiag;
         if (is_zero(piv)) piv = mk(eps3, 0.0);

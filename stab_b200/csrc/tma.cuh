@@ -23,6 +23,9 @@ __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.as
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   asm volatile(
       "{\n"
@@ -32,6 +35,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// the same wait as a pure polling loop (mbarrier.test_wait never suspends the thread): for barriers completed by plain
+// arrivals of other warps, where the wake-up of a thread suspended in try_wait was measured at ~10 us
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SPIN_%=:\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SPUN_%=;\n"
+      "bra SPIN_%=;\n"
+      "SPUN_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
