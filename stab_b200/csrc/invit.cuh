@@ -587,7 +587,7 @@ struct Invit2Slot {
           Invit2Pub* pb = pub + 2 * pi + (k & 1);
           if (role == 1) {
             bool sw; cplx mq, yk;
-            invit_pivot(acol[k], cdiag, ydiag, eps3, sw, mq, yk);
+            invit_pivot_pb(acol[k], cdiag, ydiag, eps3, sw, mq, yk);
             if (lane == 0) { pb->mq = mq; pb->yk = yk; pb->sw = sw ? 1 : 0; }
             pair_barrier(pi);
             invit_apply<NSH, (SBG >= NSH ? SBG - NSH : 0)>(k - R0, lane, acol + R0, lm, sw, mq, yk, c, y, flags, cdiag, ydiag);
@@ -631,7 +631,7 @@ k_invit2(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restr
   const double eps3 = fmax(SD_ULP * hnorm[p], smlnum);
   const double growto = 0.1 / sqrt((double)n);
   __shared__ uint64_t bars[2];                              // transaction barriers of the two staging buffers
-  if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bars[0], INVIT2_CB); mbar_init(&bars[1], INVIT2_CB); mbar_fence_init(); }   // one arrival per issuing lane
   __syncthreads();
   unsigned par = 0u;
 
@@ -651,20 +651,13 @@ k_invit2(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restr
     struct Stager {
       const cplx* H; cplx* sH; uint64_t* bars; unsigned* parity; int n;
       __device__ void operator()(int B, int bufi) const {
-        if (threadIdx.x != 0) return;
-        cplx* dst = sH + (size_t)bufi * INVIT2_CB * n;
-        unsigned bytes = 0;
-        for (int q = 0; q < INVIT2_CB; ++q) {
-          const int k = INVIT2_CB * B + q;
-          if (k >= 1 && k <= n - 1) bytes += (unsigned)(k + 1) * 16u;
-        }
+        if ((threadIdx.x & 31) != 0 || (threadIdx.x >> 5) >= INVIT2_CB) return;   // lane 0 of warp q issues column q
+        const int q = threadIdx.x >> 5, k = INVIT2_CB * B + q;
+        const bool ok = k >= 1 && k <= n - 1;
+        const unsigned bytes = ok ? (unsigned)(k + 1) * 16u : 0u;
         fence_async_smem();
         mbar_arrive_expect_tx(bars + bufi, bytes);
-        for (int q = 0; q < INVIT2_CB; ++q) {
-          const int k = INVIT2_CB * B + q;
-          if (k < 1 || k > n - 1) continue;
-          bulk_g2s(dst + (size_t)q * n, H + (size_t)(k - 1) * n, (unsigned)(k + 1) * 16u, bars + bufi);
-        }
+        if (ok) bulk_g2s(sH + ((size_t)bufi * INVIT2_CB + q) * n, H + (size_t)(k - 1) * n, bytes, bars + bufi);
       }
       __device__ void wait(int bufi) const { mbar_wait(bars + bufi, (*parity >> bufi) & 1u); *parity ^= 1u << bufi; }
     };
@@ -700,29 +693,10 @@ k_invit2(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restr
         if (r < m) { wy[r] = y[s]; wc[r] = c[s]; wf[r] = (unsigned char)((flags >> s) & 1u); }
       }
       pair_barrier(pi);
-      if (role == 0 && lane == 0) {
+      if (role == 0) {                                      // warp F: the recurrence as a warp-wide scan (invit_recurrence_scan)
         cplx piv = cdiag;
         if (is_zero(piv)) piv = mk(eps3, 0.0);
-        cplx prev = cdiv(ydiag, piv);                       // current value of y[k-1]
-        int k = 1;
-        for (; k + 3 < m; k += 4) {                         // loads of four rows in flight, recurrence in order
-          const cplx y0 = wy[k], y1 = wy[k + 1], y2 = wy[k + 2], y3 = wy[k + 3];
-          const cplx m0 = wc[k], m1 = wc[k + 1], m2 = wc[k + 2], m3 = wc[k + 3];
-          const bool f0 = wf[k] != 0, f1 = wf[k + 1] != 0, f2 = wf[k + 2] != 0, f3 = wf[k + 3] != 0;
-          cplx t, fin;
-          t = y0 - m0 * prev; fin = f0 ? t : prev; prev = f0 ? prev : t; wy[k - 1] = fin;
-          t = y1 - m1 * prev; fin = f1 ? t : prev; prev = f1 ? prev : t; wy[k] = fin;
-          t = y2 - m2 * prev; fin = f2 ? t : prev; prev = f2 ? prev : t; wy[k + 1] = fin;
-          t = y3 - m3 * prev; fin = f3 ? t : prev; prev = f3 ? prev : t; wy[k + 2] = fin;
-        }
-        for (; k < m; ++k) {
-          const cplx t = wy[k] - wc[k] * prev;
-          const bool f = wf[k] != 0;
-          const cplx fin = f ? t : prev;                    // final x[k-1]
-          prev = f ? prev : t;
-          wy[k - 1] = fin;
-        }
-        wy[m - 1] = prev;                                   // last row gets the carried value
+        invit_recurrence_scan(m, lane, wy, wc, wf, cdiv(ydiag, piv));
       }
       pair_barrier(pi);
 #pragma unroll
