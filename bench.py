@@ -617,7 +617,7 @@ def main():
     invit_ms = evec_bd.get("invit", 0.0)
     invit_flops = 8.0 * float(n) ** 3 * P
     invit_tf = invit_flops / (invit_ms * 1e-3) / 1e12 if invit_ms > 0 else 0.0
-    roofline_invit = {"kernel": "k_invit<20> (largest single kernel: one warp per eigenvalue, Hessenberg columns staged by TMA bulk copies)",
+    roofline_invit = {"kernel": "k_invit<20,1> (inverse iteration in panel / bulk form: one warp per eigenvalue, pivot chain of a staged 8-column block on the boundary slot, recorded steps applied to the rows above as a DFMA stream; columns staged by TMA bulk copies)",
                       "bound": "fp64 vector (DFMA; 33.7 TFLOP/s measured on this pool in round 1, the DGEMM figure is used as the denominator)",
                       "achieved": invit_tf, "peak": peak, "unit": "TFLOP/s", "frac": invit_tf / peak if peak else None,
                       "flops_per_step": invit_flops, "ms_per_step": invit_ms}

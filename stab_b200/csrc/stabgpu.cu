@@ -35,7 +35,7 @@ struct DevCtx { int device = 0; stabgpu_plan* cached = nullptr; StageRing ring; 
 std::vector<DevCtx> g_devs;
 int g_stage_threads = 4;      // host threads that copy one staged chunk into the caller's (pageable) array
 int g_pin_mode = 1;           // 1: pageable destinations go through the pinned staging ring; 0: plain cudaMemcpyAsync into them
-struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int qr_nw = 32, qr_nibble = 14; /* deflation window of the QR kernel (0: classic deflation only) and ZLAQR0's NIBBLE */ int hess_streams = 1; int evec_mode = 1; int lu_mode = 1; /* 1: blocked LU with DMMA updates, 0: v1 one-CTA kernel */ int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
+struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int qr_nw = 32, qr_nibble = 14; /* deflation window of the QR kernel (0: classic deflation only) and ZLAQR0's NIBBLE */ int hess_streams = 1; int hess_graph = 1; /* replay the Hessenberg stage as one CUDA graph (0: individual launches) */ int evec_mode = 1; int lu_mode = 1; /* 1: blocked LU with DMMA updates, 0: v1 one-CTA kernel */ int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
 bool g_qrprof_on = false;
@@ -117,6 +117,8 @@ struct stabgpu_plan {
   std::vector<cudaEvent_t> evA, evB;
   bool stop_after_lu = false;             // debug: assembly + LU reduce only (stabgpu_debug_spatial_reduce)
   bool prof_hess = false;                 // record events around every Hessenberg kernel class (bench breakdown)
+  cudaGraphExec_t hess_graph = nullptr;   // the ~1400 launches of the blocked reduction, captured on the first execute
+  int hess_graph_mode = -1; long long hess_graph_launches = 0;
   std::vector<cudaEvent_t> pev; size_t pev_n = 0; std::vector<int> pev_cls;
   float hess_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // panel_step, gemv, gemm, other, invit, back-transformation GEMM, finalize, -
   // grid / profile
@@ -345,7 +347,25 @@ int run_hessenberg(stabgpu_plan* pl) {
   // software pipeline over the two halves: the GEMV phases (memory bound) of A and B never overlap each
   // other, each overlaps the tensor-core phase of the other half
   const bool two = half < np;
-  for (int p = 0; p < pl->hbP; ++p) {
+  // One stream, no profiling marks: the schedule depends only on (N, npts, hess_mode) -- every data-dependent quantity
+  // (ilo/ihi, the panel extents) is read on the device -- so it is captured once per plan and replayed as a CUDA graph.
+  const bool graphed = g_tune.hess_graph && !two && !pl->prof_hess;
+  if (graphed && pl->hess_graph && pl->hess_graph_mode == g_tune.hess_mode * 65536 + g_tune.hess_threads) {
+    CU(cudaGraphLaunch(pl->hess_graph, s));
+    pl->launches += pl->hess_graph_launches;
+    return 0;
+  }
+  const long long launches0 = pl->launches;
+  if (graphed) {
+    if (pl->hess_graph) { cudaGraphExecDestroy(pl->hess_graph); pl->hess_graph = nullptr; }
+    CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  }
+  int rc = 0;
+  for (int p = 0; p < pl->hbP && !rc; ++p) {
+    if (!two) {
+      rc = hess_panel(pl, hb, half, s, p, mma, 1) || hess_panel(pl, hb, half, s, p, mma, 2);
+      continue;
+    }
     if (two && p > 0) CU(cudaStreamWaitEvent(s, pl->evB[p - 1], 0));
     if (hess_panel(pl, hb, half, s, p, mma, 1)) return 1;
     if (two) {
@@ -359,6 +379,19 @@ int run_hessenberg(stabgpu_plan* pl) {
       if (hess_panel(pl, hb2, np - half, pl->stream2, p, mma, 2)) return 1;
     }
   }
+  if (graphed) {
+    cudaGraph_t gr = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s, &gr);
+    if (rc || ce != cudaSuccess) { if (gr) cudaGraphDestroy(gr); return rc ? rc : fail(cudaGetErrorString(ce)); }
+    const cudaError_t ci = cudaGraphInstantiate(&pl->hess_graph, gr, 0);
+    cudaGraphDestroy(gr);
+    if (ci != cudaSuccess) { pl->hess_graph = nullptr; return fail(cudaGetErrorString(ci)); }
+    pl->hess_graph_mode = g_tune.hess_mode * 65536 + g_tune.hess_threads;
+    pl->hess_graph_launches = pl->launches - launches0;
+    CU(cudaGraphLaunch(pl->hess_graph, s));
+    return 0;
+  }
+  if (rc) return rc;
   if (half < np) { CU(cudaEventRecord(pl->evJoin, pl->stream2)); CU(cudaStreamWaitEvent(s, pl->evJoin, 0)); }
   return 0;
 }
@@ -711,6 +744,7 @@ int stabgpu_debug_set_qr_steps(int steps) { if (steps > 0) g_tune.qr_steps = ste
 int stabgpu_debug_set_qr_aed(int nw, int nibble) { if (nw >= 0) g_tune.qr_nw = nw; if (nibble >= 0) g_tune.qr_nibble = nibble; return 0; }
 int stabgpu_set_qr_deflation(int window, int nibble) { return stabgpu_debug_set_qr_aed(window, nibble); }
 int stabgpu_set_evec_mode(int mode) { g_tune.evec_mode = mode; return 0; }
+int stabgpu_debug_set_hess_graph(int on) { g_tune.hess_graph = on ? 1 : 0; return 0; }
 int stabgpu_set_lu_mode(int mode) { g_tune.lu_mode = mode; return 0; }
 
 int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads) {
@@ -888,6 +922,7 @@ int stabgpu_plan_destroy(stabgpu_plan* pl) {
   for (auto& d : g_devs) if (d.cached == pl) d.cached = nullptr;
   int prev = 0;
   const bool switched = cudaGetDevice(&prev) == cudaSuccess && prev != pl->device && cudaSetDevice(pl->device) == cudaSuccess;
+  if (pl->hess_graph) cudaGraphExecDestroy(pl->hess_graph);
   if (pl->stream) cudaStreamDestroy(pl->stream);
   if (pl->stream2) cudaStreamDestroy(pl->stream2);
   if (pl->evFork) cudaEventDestroy(pl->evFork);

@@ -303,3 +303,27 @@ def test_panel_bulk_inverse_iteration_on_the_ts_operator():
     d = np.abs(ev1 - ev3).max(axis=1)
     assert d[phys].max() < 1e-8
     assert np.median(d) < 1e-12
+
+
+def test_hessenberg_graph_replay_is_bit_identical():
+    """The blocked Hessenberg stage replayed as one CUDA graph (default; captured on a plan's first execute) against the
+    same ~1400 kernels launched one by one: identical eigenvalues and vectors on the first (capture) and on later (replay)
+    executes of the cached plan, for two batches of the same shape with different data."""
+    rng = np.random.default_rng(77)
+    n, b = 200, 5
+    A1 = (rng.standard_normal((b, n, n)) + 1j * rng.standard_normal((b, n, n))) / np.sqrt(n)
+    A2 = (rng.standard_normal((b, n, n)) + 1j * rng.standard_normal((b, n, n))) / np.sqrt(n)
+    lib = sb.lib()
+    lib.stabgpu_debug_set_hess_graph.argtypes = [C.c_int]
+    got = {}
+    try:
+        for on in (1, 0):
+            lib.stabgpu_debug_set_hess_graph(on)
+            got[on] = [sb.zgeev_batch(A, want_vectors=True) for A in (A1, A2, A1)]
+    finally:
+        lib.stabgpu_debug_set_hess_graph(1)
+    for k in range(3):
+        assert np.all(got[1][k][2] == 0)
+        assert np.array_equal(got[1][k][0], got[0][k][0])
+        assert np.array_equal(got[1][k][1], got[0][k][1])
+    assert np.array_equal(got[1][0][0], got[1][2][0])
