@@ -18,3 +18,8 @@ pl = sb.Plan(2, c.params, c.vm, c.deta, c.d2eta, P, want_vectors=vec, h5=c.h5)
 pl.upload(om, om * 0)
 pl.execute()
 print({k: round(v, 1) for k, v in pl.stage_times().items()})
+if vec and os.environ.get("STAB_BREAKDOWN"):
+    pl.profile_hessenberg(True)
+    pl.execute()
+    print("hessenberg", {k: round(v, 1) for k, v in pl.profile_hessenberg(False).items()})
+    print("eigenvectors", {k: round(v, 1) for k, v in pl.profile_eigvec().items()})

@@ -250,22 +250,22 @@ SD_DEV void invit_bulk_step(int lane, const cplx* __restrict__ acol, bool sw, cp
   }
 }
 
-template <int NS, int SB>
+template <int NS, int SB, int CBK = INVIT_CB>
 struct InvitGroup {
   template <class Prefetch>
   SD_DEV static void run(int n, int m, bool live, int lane, cplx* sH, InvitRec* rec, cplx lm, double eps3,
                          cplx (&c)[NS], cplx (&y)[NS], unsigned& flags, cplx& cdiag, cplx& ydiag, int& buf, Prefetch& prefetch) {
     constexpr int S1 = SB > 0 ? SB - 1 : 0;
 #pragma unroll 1
-    for (int bq = 3; bq >= 0; --bq) {
-      const int B = 4 * SB + bq;
-      if (8 * B > n - 1) continue;                       // block above the matrix (uniform)
+    for (int bq = 32 / CBK - 1; bq >= 0; --bq) {
+      const int B = (32 / CBK) * SB + bq;
+      if (CBK * B > n - 1) continue;                       // block above the matrix (uniform)
       prefetch.wait(buf);                                // block B landed (transaction barrier of its buffer)
       __syncthreads();                                   // everyone left block B+1
       if (B > 0) prefetch(B - 1, buf ^ 1);
-      const cplx* tile = sH + (size_t)buf * INVIT_CB * n;
-      const int k0 = 8 * B;
-      const int qhi = live ? min(INVIT_CB - 1, m - 1 - k0) : -1;   // steps k0+qhi .. k0+qlo of this block are this eigenvalue's
+      const cplx* tile = sH + (size_t)buf * CBK * n;
+      const int k0 = CBK * B;
+      const int qhi = live ? min(CBK - 1, m - 1 - k0) : -1;   // steps k0+qhi .. k0+qlo of this block are this eigenvalue's
       const bool edge = SB > 0 && bq == 0;               // q = 0 is the slot-edge step k = 32 SB
       const int qlo = (B == 0 || edge) ? 1 : 0;          // k = 0 is no step; the edge step runs apart
       unsigned swm = 0u;
@@ -310,11 +310,11 @@ struct InvitGroup {
       __syncwarp();                                      // records read before the next block's panel rewrites them
       buf ^= 1;
     }
-    InvitGroup<NS, SB - 1>::run(n, m, live, lane, sH, rec, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+    InvitGroup<NS, SB - 1, CBK>::run(n, m, live, lane, sH, rec, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
   }
 };
-template <int NS>
-struct InvitGroup<NS, -1> {
+template <int NS, int CBK>
+struct InvitGroup<NS, -1, CBK> {
   template <class Prefetch>
   SD_DEV static void run(int, int, bool, int, cplx*, InvitRec*, cplx, double, cplx (&)[NS], cplx (&)[NS], unsigned&, cplx&, cplx&, int&, Prefetch&) {}
 };
@@ -613,13 +613,136 @@ struct Invit2Slot<NSH, -1> {
                          int&, Prefetch&) {}
 };
 
-// grid: (ceil(n / (4*rounds)), batch), block 256.  smem: 2 * INVIT2_CB * n complex + INVIT2_PAIRS * n bytes.  n <= 64 NSH.
+// ---------------------------------------------------------------------------------------------------------------
+// Two warps per eigenvalue in the panel / bulk form (k_invit2<NSH, 1>, the default for 640 < n <= 1280).  While the pivot
+// row is in P's range (steps k >= R0) P runs the PANEL of a staged 4-column block on its boundary slot exactly as the
+// one-warp kernel does (local row numbers k - R0), publishes the four (mq, yk) records and the interchange bits through
+// shared memory, and the pair meets ONCE per block (the per-step form met once per step); then P applies the recorded
+// steps to its slots below the boundary and F to all of its slots.  At k = R0 the row above the pivot is F's last one:
+// F takes that step -- P hands over the carried diagonal, F updates its last slot, returns the multiplier that belongs to
+// P's row R0 (second meeting of that block) and applies the step to its other slots.  Below R0 P's rows are finished and
+// F runs the one-warp panel / bulk groups; P only keeps the staging protocol going.
+struct Invit2Mail { InvitRec rec[INVIT2_CB]; InvitRec edge; cplx cdiag, ydiag; unsigned swm; int esw; int pad[2]; };
+
+// the step k = R0 on F's last slot: as invit_panel_edge, the multiplier goes back to P instead of into an own register
 template <int NSH>
+SD_DEV void invit_cross_edge(int lane, cplx ak, cplx a, cplx lm, double eps3, cplx (&c)[NSH], cplx (&y)[NSH], cplx& cdiag, cplx& ydiag,
+                             bool& sw, cplx& mq, cplx& yk) {
+  invit_pivot_pb(ak, cdiag, ydiag, eps3, sw, mq, yk);
+  if (lane == 31) a -= lm;
+  const cplx cr = c[NSH - 1], yr = y[NSH - 1];
+  const cplx q = sw ? a : cr, p = sw ? cr : a;
+  cplx cn = p, yn = yr;
+  fms_acc(cn, mq, q);
+  fms_acc(yn, yk, q);
+  c[NSH - 1] = cn; y[NSH - 1] = yn;
+  cdiag = shfl_c(cn, 31);
+  ydiag = shfl_c(yn, 31);
+}
+
+template <int NSH, int SBL>                                  // SBL: P's local slot group, steps k = R0 + 32 SBL + 31 .. R0 + 32 SBL
+struct Invit2Group {
+  template <class Prefetch>
+  SD_DEV static void run(int n, int m, bool live, int lane, int role, int pi, cplx* sH, Invit2Mail* mail, cplx lm, double eps3,
+                         cplx (&c)[NSH], cplx (&y)[NSH], unsigned& flags, cplx& cdiag, cplx& ydiag, int& buf, Prefetch& prefetch) {
+    constexpr int R0 = 32 * NSH;
+    constexpr int S1 = SBL > 0 ? SBL - 1 : 0;
+    constexpr int NBLK = 32 / INVIT2_CB;
+#pragma unroll 1
+    for (int bq = NBLK - 1; bq >= 0; --bq) {
+      const int B = NBLK * (NSH + SBL) + bq;
+      if (INVIT2_CB * B > n - 1) continue;                 // block above the matrix (uniform)
+      prefetch.wait(buf);
+      __syncthreads();                                     // everyone left block B+1
+      if (B > 0) prefetch(B - 1, buf ^ 1);
+      const cplx* tile = sH + (size_t)buf * INVIT2_CB * n;
+      const int k0 = INVIT2_CB * B;
+      const int qhi = live ? min(INVIT2_CB - 1, m - 1 - k0) : -1;   // the same for both warps of a pair
+      const bool edgeP = SBL > 0 && bq == 0;               // q = 0 is P's own slot edge
+      const bool edgeF = SBL == 0 && bq == 0;              // q = 0 is the step k = R0, taken by F
+      const int qlo = (edgeP || edgeF) ? 1 : 0;
+      if (role == 1) {
+        unsigned swm = 0u;
+        if (qhi >= qlo) {
+          cplx ak = tile[(size_t)qhi * n + k0 + qhi], a = tile[(size_t)qhi * n + R0 + 32 * SBL + lane];
+#pragma unroll 1
+          for (int q = qhi; q >= qlo; --q) {
+            const int qn = q > qlo ? q - 1 : q;
+            const cplx ak_n = tile[(size_t)qn * n + k0 + qn], a_n = tile[(size_t)qn * n + R0 + 32 * SBL + lane];
+            bool sw; cplx mq, yk;
+            invit_panel_step<NSH, SBL>(k0 + q - R0, lane, ak, a, lm, eps3, c, y, flags, cdiag, ydiag, sw, mq, yk);
+            if (sw) swm |= 1u << q;
+            if (lane == 0) { mail->rec[q].mq = mq; mail->rec[q].yk = yk; }
+            ak = ak_n; a = a_n;
+          }
+        }
+        __syncwarp();
+        if (edgeP && qhi >= 0) {                           // bring P's slot SBL-1 up to date, then the edge step on it
+#pragma unroll 1
+          for (int q = qhi; q >= 1; --q)
+            invit_bulk_step<NSH, S1, SBL>(lane, tile + (size_t)q * n + R0, (swm >> q) & 1u, mail->rec[q].mq, mail->rec[q].yk, c, y);
+          bool sw; cplx mq, yk;
+          invit_panel_edge<NSH, SBL>(lane, tile[k0], tile[R0 + 32 * S1 + lane], lm, eps3, c, y, flags, cdiag, ydiag, sw, mq, yk);
+          if (sw) swm |= 1u;
+          if (lane == 0) { mail->rec[0].mq = mq; mail->rec[0].yk = yk; }
+        }
+        if (lane == 0) { mail->swm = swm; mail->cdiag = cdiag; mail->ydiag = ydiag; }
+        pair_barrier(pi);                                  // (A) the block's records are published
+        if (edgeP) {
+#pragma unroll 1
+          for (int q = qhi; q >= 0; --q)
+            invit_bulk_step<NSH, 0, S1>(lane, tile + (size_t)q * n + R0, (swm >> q) & 1u, mail->rec[q].mq, mail->rec[q].yk, c, y);
+        } else {
+#pragma unroll 1
+          for (int q = qhi; q >= qlo; --q)
+            invit_bulk_step<NSH, 0, SBL>(lane, tile + (size_t)q * n + R0, (swm >> q) & 1u, mail->rec[q].mq, mail->rec[q].yk, c, y);
+        }
+        if (edgeF) {
+          pair_barrier(pi);                                // (B) F has taken the step k = R0
+          if (qhi >= 0 && lane == 0) {                     // its multiplier belongs to row R0: slot 0, lane 0
+            c[0] = mail->edge.mq; y[0] = mail->edge.yk;
+            if (mail->esw) flags |= 1u;
+          }
+        }
+      } else {
+        pair_barrier(pi);                                  // (A)
+        const unsigned swm = mail->swm;
+#pragma unroll 1
+        for (int q = qhi; q >= (edgeF ? 1 : 0); --q)       // P's own slot edge is an ordinary step for F's rows
+          invit_bulk_step<NSH, 0, NSH>(lane, tile + (size_t)q * n, (swm >> q) & 1u, mail->rec[q].mq, mail->rec[q].yk, c, y);
+        if (edgeF) {
+          bool sw = false; cplx mq = mk(0.0, 0.0), yk = mk(0.0, 0.0);
+          if (qhi >= 0) {
+            cdiag = mail->cdiag; ydiag = mail->ydiag;      // P's carried diagonal after its last step
+            invit_cross_edge<NSH>(lane, tile[k0], tile[32 * (NSH - 1) + lane], lm, eps3, c, y, cdiag, ydiag, sw, mq, yk);
+            if (lane == 0) { mail->edge.mq = mq; mail->edge.yk = yk; mail->esw = sw ? 1 : 0; }
+          }
+          pair_barrier(pi);                                // (B)
+          if (qhi >= 0) invit_bulk_step<NSH, 0, NSH - 1>(lane, tile, sw, mq, yk, c, y);
+        }
+      }
+      buf ^= 1;
+    }
+    Invit2Group<NSH, SBL - 1>::run(n, m, live, lane, role, pi, sH, mail, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+  }
+};
+template <int NSH>
+struct Invit2Group<NSH, -1> {
+  template <class Prefetch>
+  SD_DEV static void run(int, int, bool, int, int, int, cplx*, Invit2Mail*, cplx, double, cplx (&)[NSH], cplx (&)[NSH], unsigned&, cplx&, cplx&,
+                         int&, Prefetch&) {}
+};
+
+// grid: (ceil(n / (4*rounds)), batch), block 256.  smem: 2 * INVIT2_CB * n complex + INVIT2_PAIRS * n bytes.  n <= 64 NSH.
+// PB = 1: panel / bulk form (default), PB = 0: the per-step form (evec_mode 3).
+template <int NSH, int PB>
 __global__ void __launch_bounds__(INVIT2_PAIRS * 64, 1)
 k_invit2(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restrict__ lam, const int* __restrict__ kr,
          const double* __restrict__ hnorm, cplx* __restrict__ Y, size_t ystride, int* __restrict__ bad, int rounds) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Invit2Pub pub[2 * INVIT2_PAIRS];
+  __shared__ Invit2Mail mails[PB ? INVIT2_PAIRS : 1];
+  __shared__ InvitRec recs2[PB ? INVIT2_PAIRS * INVIT2_CB : 1];      // F's own records below R0 (one-warp groups)
   __shared__ double vnorm[2 * INVIT2_PAIRS];
   constexpr int R0 = 32 * NSH;
   cplx* sH = reinterpret_cast<cplx*>(smem_raw);            // [2][INVIT2_CB][n]
@@ -679,7 +802,14 @@ k_invit2(const cplx* __restrict__ Hh, size_t hstride, int n, const cplx* __restr
     __syncthreads();                                        // previous round finished with both buffers
     int buf = 0;
     prefetch((n - 1) / INVIT2_CB, 0);
-    Invit2Slot<NSH, 2 * NSH - 1>::run(n, m, live, lane, role, pi, sH, pub, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+    if constexpr (PB != 0) {
+      Invit2Group<NSH, NSH - 1>::run(n, m, live, lane, role, pi, sH, mails + pi, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+      // below R0: F alone (P only waits, synchronises and issues its staging copy)
+      InvitGroup<NSH, NSH - 1, INVIT2_CB>::run(n, m, live && role == 0, lane, sH, recs2 + pi * INVIT2_CB, lm, eps3, c, y, flags, cdiag, ydiag, buf,
+                                               prefetch);
+    } else {
+      Invit2Slot<NSH, 2 * NSH - 1>::run(n, m, live, lane, role, pi, sH, pub, lm, eps3, c, y, flags, cdiag, ydiag, buf, prefetch);
+    }
     // ---- x = T_{m-1} ... T_1 y: the first-order recurrence of the single-warp kernel, run by lane 0 of warp F over
     // the rows of both warps (parked in the idle staging buffers) ----
     __syncthreads();                                        // every warp has finished reading the staged columns

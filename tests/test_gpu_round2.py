@@ -262,13 +262,13 @@ def test_qr_early_deflation_against_classic_deflation():
         assert (d[phys] / np.maximum(np.abs(got[0][k][phys]), 1e-3)).max() < 1e-9
 
 
-@pytest.mark.parametrize("n,batch", [(40, 3), (97, 2), (200, 2), (417, 1), (640, 2)])
+@pytest.mark.parametrize("n,batch", [(40, 3), (97, 2), (200, 2), (417, 1), (640, 2), (641, 1), (700, 2), (1000, 1), (1025, 1), (1280, 2)])
 def test_panel_bulk_inverse_iteration_against_per_step_form(n, batch):
     """The panel / bulk form of the register-resident inverse iteration (default, k_invit<NS, 1>: pivot chain of a staged
     8-column block first, recorded steps applied to the rows above afterwards) against the per-step form (evec_mode 3,
     the round-1 kernel): every entry sees the same operations in the same order, only the reciprocal differs in its last
     bits, so the vectors agree to rounding; residuals at the same level; on the Ny=64 TS operator (leading blocks kr < n
-    from ZGEBAL's isolated rows) as well."""
+    from ZGEBAL's isolated rows) as well.  Orders above 640 run the two-warp kernels (k_invit2<NSH, 1> against <NSH, 0>)."""
     rng = np.random.default_rng(4000 + n)
     A = (rng.standard_normal((batch, n, n)) + 1j * rng.standard_normal((batch, n, n))) / np.sqrt(n)
     w1, V1, i1 = sb.zgeev_batch(A, want_vectors=True)
