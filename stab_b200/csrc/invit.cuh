@@ -189,22 +189,31 @@ SD_DEV void invit_pivot_pb(cplx ak, cplx cdiag, cplx ydiag, double eps3, bool& s
   yk = ty * rd;
 }
 
-// one panel step k (k & 31 != 0) of slot group SB: pivot, boundary slot SB, next carried diagonal
+// one panel step k (k & 31 != 0) of slot group SB: pivot, boundary slot SB, next carried diagonal.
+// Branch-free and with nothing but two FMA levels between the multiplier and the shuffle that feeds the next pivot: the
+// operands of   c' = P - mq Q,  y' = Y - yk Q   are chosen per lane class BEFORE the pivot chain delivers mq --
+//   rows below the pivot row : (P, Q) = interchanged ? (c, a) : (a, c),  Y = y      the elimination proper
+//   the pivot row            : (P, Q, Y) = (0, -1, 0)                               c' = mq, y' = yk exactly: the multiplier is parked
+//   finished rows            : (P, Q, Y) = (c, 0, y)                                unchanged
+// and the interchange bit, known early in the chain, picks between the two variants.
 template <int NS, int SB>
 SD_DEV void invit_panel_step(int k, int lane, cplx ak, cplx a, cplx lm, double eps3, cplx (&c)[NS], cplx (&y)[NS], unsigned& flags,
                              cplx& cdiag, cplx& ydiag, bool& sw, cplx& mq, cplx& yk) {
   const int kk = k & 31;
-  invit_pivot_pb(ak, cdiag, ydiag, eps3, sw, mq, yk);
+  const bool below = lane < kk, at = lane == kk;
   if (lane == kk - 1) a -= lm;
   const cplx cr = c[SB], yr = y[SB];
-  const cplx q = sw ? a : cr, p = sw ? cr : a;
-  cplx cn = p, yn = yr;
+  const cplx unit = mk(at ? -1.0 : 0.0, 0.0);
+  const cplx qa = below ? a : unit, qc = below ? cr : unit;
+  const cplx pa = at ? mk(0.0, 0.0) : cr, pc = below ? a : pa;
+  const cplx y0 = at ? mk(0.0, 0.0) : yr;
+  invit_pivot_pb(ak, cdiag, ydiag, eps3, sw, mq, yk);
+  const cplx q = sw ? qa : qc, p = sw ? pa : pc;
+  cplx cn = p, yn = y0;
   fms_acc(cn, mq, q);
   fms_acc(yn, yk, q);
-  const bool below = lane < kk, at = lane == kk;
-  c[SB] = below ? cn : (at ? mq : cr);
-  y[SB] = below ? yn : (at ? yk : yr);
-  if (at && sw) flags |= (1u << SB);
+  c[SB] = cn; y[SB] = yn;
+  flags |= (at && sw) ? (1u << SB) : 0u;
   cdiag = shfl_c(cn, kk - 1);
   ydiag = shfl_c(yn, kk - 1);
 }
@@ -272,7 +281,7 @@ struct InvitGroup {
       // ---- panel ----
       if (qhi >= qlo) {
         cplx ak = tile[(size_t)qhi * n + k0 + qhi], a = tile[(size_t)qhi * n + 32 * SB + lane];
-#pragma unroll 1
+#pragma unroll 2
         for (int q = qhi; q >= qlo; --q) {
           const int k = k0 + q;
           const int qn = q > qlo ? q - 1 : q;            // next step's entries: loaded ahead of this step's pivot chain
