@@ -75,7 +75,8 @@ int stabgpu_set_qr_deflation(int window, int nibble);
  * scalar-FMA GEMM (validation of the tensor-core path); 0 the unblocked one-CTA-per-matrix kernel of v1; 5 as 1 with the right and
  * left trailing updates fused into one rank-64 pass (measured slower, kept as a validated variant) */
 int stabgpu_set_hess_mode(int mode);
-/* eigenvector stage variant: 1 (default) register-resident inverse iteration + tensor-core back-transformation; 0 the v1 warp kernel */
+/* eigenvector stage variant: 1 (default) register-resident inverse iteration in panel / bulk form + tensor-core back-transformation;
+ * 3 the same with the per-step inverse iteration of round 1 (validation of the panel / bulk form); 0 the v1 warp kernel */
 int stabgpu_set_evec_mode(int mode);
 /* spatial LU reduce variant (ZGETRF + 2 x ZGETRS, spatial.f90:978-1004): 1 (default) blocked LU with DMMA rank-32
  * updates; 0 the v1 one-CTA-per-matrix kernel */
