@@ -278,14 +278,17 @@ struct InvitGroup {
       const bool edge = SB > 0 && bq == 0;               // q = 0 is the slot-edge step k = 32 SB
       const int qlo = (B == 0 || edge) ? 1 : 0;          // k = 0 is no step; the edge step runs apart
       unsigned swm = 0u;
+      // the boundary slot is read whole; rows past the end of the matrix are clamped to the last row (their values are never
+      // selected), so that the load cannot reach into the other buffer while its bulk copies are in flight
+      const int rb = min(32 * SB + lane, n - 1);
       // ---- panel ----
       if (qhi >= qlo) {
-        cplx ak = tile[(size_t)qhi * n + k0 + qhi], a = tile[(size_t)qhi * n + 32 * SB + lane];
+        cplx ak = tile[(size_t)qhi * n + k0 + qhi], a = tile[(size_t)qhi * n + rb];
 #pragma unroll 2
         for (int q = qhi; q >= qlo; --q) {
           const int k = k0 + q;
           const int qn = q > qlo ? q - 1 : q;            // next step's entries: loaded ahead of this step's pivot chain
-          const cplx ak_n = tile[(size_t)qn * n + k0 + qn], a_n = tile[(size_t)qn * n + 32 * SB + lane];
+          const cplx ak_n = tile[(size_t)qn * n + k0 + qn], a_n = tile[(size_t)qn * n + rb];
           bool sw; cplx mq, yk;
           invit_panel_step<NS, SB>(k, lane, ak, a, lm, eps3, c, y, flags, cdiag, ydiag, sw, mq, yk);
           if (sw) swm |= 1u << q;
@@ -673,11 +676,12 @@ struct Invit2Group {
       if (role == 1) {
         unsigned swm = 0u;
         if (qhi >= qlo) {
-          cplx ak = tile[(size_t)qhi * n + k0 + qhi], a = tile[(size_t)qhi * n + R0 + 32 * SBL + lane];
+          const int rb = min(R0 + 32 * SBL + lane, n - 1);  // as in InvitGroup: never past the matrix
+          cplx ak = tile[(size_t)qhi * n + k0 + qhi], a = tile[(size_t)qhi * n + rb];
 #pragma unroll 1
           for (int q = qhi; q >= qlo; --q) {
             const int qn = q > qlo ? q - 1 : q;
-            const cplx ak_n = tile[(size_t)qn * n + k0 + qn], a_n = tile[(size_t)qn * n + R0 + 32 * SBL + lane];
+            const cplx ak_n = tile[(size_t)qn * n + k0 + qn], a_n = tile[(size_t)qn * n + rb];
             bool sw; cplx mq, yk;
             invit_panel_step<NSH, SBL>(k0 + q - R0, lane, ak, a, lm, eps3, c, y, flags, cdiag, ydiag, sw, mq, yk);
             if (sw) swm |= 1u << q;
