@@ -3,17 +3,20 @@
 // ZGEEV('N','V') the reference calls (temporal.f90:803, spatial.f90:1043) by the ZHSEIN/ZLAEIN
 // idea -- one solve with (H - lambda I) per eigenvalue, started from a vector of size eps.
 //
-// One WARP per eigenvalue, 8 eigenvalues per CTA advancing in lock step through the elimination
+// One WARP per eigenvalue, 8 eigenvalues per CTA advancing block by block through the elimination
 //   for k = m-1 .. 1:  combine Hessenberg column k-1 with the carried column (column operations
 //                      from the bottom row up, with column interchanges -- see evec.cuh)
 // * the carried column c and the right-hand side y live in REGISTERS: lane l owns rows
 //   r = 32 s + l (s = 0..NS-1), so every update is two complex FMAs on registers;
 // * the Hessenberg columns are staged ONCE per CTA through shared memory in double-buffered
-//   8-column blocks with cp.async (LDGSTS), shared by the 8 warps: global/L2 traffic is
-//   (n^2/2 * 16 B) per 8 eigenvalues instead of per eigenvalue;
+//   8-column blocks by bulk copies on the TMA engine (cp.async.bulk + mbarrier transaction counts,
+//   tma.cuh), shared by the 8 warps: global/L2 traffic is (n^2/2 * 16 B) per 8 eigenvalues;
 // * the pivots travel by warp shuffles; the multipliers overwrite the dead entries of c.
+// Two forms of the step loop: the per-step form (InvitSlot, round 1; validation switch evec_mode 3)
+// and the panel / bulk form (InvitGroup, the default; described at its definition).  Orders above
+// 640 use two warps per eigenvalue (k_invit2).
 // The vectors come out in the Hessenberg basis (zero below the diagonal block's end kr);
-// the back-transformation by Q is a tensor-core GEMM (k_bt_* kernels), then k_vec_finalize.
+// the back-transformation by Q is a tensor-core GEMM (k_gemm_pipe<BT_*>), then k_vec_finalize.
 #pragma once
 #include "common.cuh"
 #include "tma.cuh"
@@ -23,15 +26,7 @@ namespace stab {
 
 constexpr int INVIT_WARPS = 8;
 constexpr int INVIT_CB = 8;        // columns per staged block
-constexpr int INVIT_PAD = 512;     // the branch-free boundary update reads a full 32-row slot: up to 31 entries past a column's end
-
-SD_DEV void cp_async16(void* smem, const void* gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
-SD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-SD_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+constexpr int INVIT_PAD = 512;     // slack behind the staging buffers (the branch-free boundary update reads whole 32-row slots)
 
 SD_DEV cplx shfl_c(cplx v, int src) { return mk(__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)); }
 
