@@ -635,7 +635,7 @@ def main():
                 "call": "stabgpu_temporal_batch, pinned host buffers (direct DMA under the eigenvector stage)",
                 "pageable": {"value": e2e_pageable_val, "unit": "eigensolves/s",
                              "call": "the same call with pageable (numpy) destination arrays: vectors staged through the library's "
-                                     "pinned ring (4 x 64 MB, 4 copy threads)", "bit_identical_to_pinned": same_bits}},
+                                     "pinned ring (4 x 64 MB, host cores / devices copy threads, 2..8)", "bit_identical_to_pinned": same_bits}},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_gemv": roofline_gemv,

@@ -57,7 +57,7 @@ int stabgpu_device_count(void);               /* devices the batch calls shard o
 /* Host staging of the eigenvector output.  A page-locked destination (cudaHostAlloc / stabgpu_host_register) receives
  * the vectors by direct DMA under the eigenvector stage; a pageable one (a Fortran `allocate`, malloc, numpy) is served
  * through a pinned staging ring inside the library (4 x 64 MB per device, DMA -> ring -> caller array by `copy_threads`
- * host threads), so the overlap survives.  pin_mode 0 disables the ring (plain cudaMemcpyAsync into pageable memory);
+ * host threads; default: host cores / devices, between 2 and 8), so the overlap survives.  pin_mode 0 disables the ring (plain cudaMemcpyAsync into pageable memory);
  * values < 0 / <= 0 keep the current setting. */
 int stabgpu_set_host_staging(int pin_mode, int copy_threads);
 int stabgpu_host_register(void* ptr, size_t bytes);    /* page-lock a caller array once (cudaHostRegister, portable) */

@@ -33,7 +33,8 @@ struct StageRing {
 };
 struct DevCtx { int device = 0; stabgpu_plan* cached = nullptr; StageRing ring; };
 std::vector<DevCtx> g_devs;
-int g_stage_threads = 4;      // host threads that copy one staged chunk into the caller's (pageable) array
+int g_stage_threads = 0;      // host threads that copy one staged chunk into the caller's (pageable) array; 0: host cores / devices, 2..8
+                              // (296 points with vectors, 16 host cores: 4 threads 970, 8 threads 987 eigensolves/s)
 int g_pin_mode = 1;           // 1: pageable destinations go through the pinned staging ring; 0: plain cudaMemcpyAsync into them
 struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int qr_nw = 32, qr_nibble = 14; /* deflation window of the QR kernel (0: classic deflation only) and ZLAQR0's NIBBLE */ int hess_streams = 1; int hess_graph = 1; /* replay the Hessenberg stage as one CUDA graph (0: individual launches) */ int evec_mode = 1; int lu_mode = 1; /* 1: blocked LU with DMMA updates, 0: v1 one-CTA kernel */ int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
@@ -945,7 +946,12 @@ int stabgpu_plan_destroy(stabgpu_plan* pl) {
 namespace {
 
 void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-  const int nt = (bytes < ((size_t)4 << 20)) ? 1 : g_stage_threads;
+  int want = g_stage_threads;
+  if (want <= 0) {
+    const int hw = (int)std::thread::hardware_concurrency(), nd = g_devs.empty() ? 1 : (int)g_devs.size();
+    want = std::min(8, std::max(2, hw / nd));
+  }
+  const int nt = (bytes < ((size_t)4 << 20)) ? 1 : want;
   if (nt <= 1) { std::memcpy(dst, src, bytes); return; }
   std::vector<std::thread> th;
   const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;
