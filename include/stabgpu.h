@@ -68,7 +68,7 @@ int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb)
 /* tuning knobs of the QR stage (window size, shifts per sweep, threads); 0 keeps the default */
 int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_threads);
 /* Aggressive early deflation of the QR stage (the ZLAQR3 step of the ZHSEQR inside the reference's ZGEEV): deflation window
- * (default 32; 0 = classic ZLAHQR-style deflation only, the round-1 algorithm -- kept as a validation switch) and ZLAQR0's
+ * (default by order: 32 up to 640, 44 above; 0 = classic ZLAHQR-style deflation only, the round-1 algorithm -- kept as a validation switch) and ZLAQR0's
  * NIBBLE in per cent (default 14).  Negative values keep the current setting. */
 int stabgpu_set_qr_deflation(int window, int nibble);
 /* Hessenberg stage variant: 1 (default) batched blocked reduction with DMMA tensor-core updates; 2 the same with a

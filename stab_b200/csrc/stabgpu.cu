@@ -36,7 +36,7 @@ std::vector<DevCtx> g_devs;
 int g_stage_threads = 0;      // host threads that copy one staged chunk into the caller's (pageable) array; 0: host cores / devices, 2..8
                               // (296 points with vectors, 16 host cores: 4 threads 970, 8 threads 987 eigensolves/s)
 int g_pin_mode = 1;           // 1: pageable destinations go through the pinned staging ring; 0: plain cudaMemcpyAsync into them
-struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int qr_nw = 32, qr_nibble = 14; /* deflation window of the QR kernel (0: classic deflation only) and ZLAQR0's NIBBLE */ int hess_streams = 1; int hess_graph = 1; /* replay the Hessenberg stage as one CUDA graph (0: individual launches) */ int evec_mode = 1; int lu_mode = 1; /* 1: blocked LU with DMMA updates, 0: v1 one-CTA kernel */ int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
+struct Tuning { int W = 64, ns = 16, qr_threads = 256, hess_threads = 512; int qr_steps = 32;   /* two CTAs per SM: 2 x 89 KB, 128 registers */ int qr_nw = -1, qr_nibble = 14; /* deflation window of the QR kernel (0: classic deflation only; -1: by order, 32 up to 640 and 44 above: 174 -> 167 ms per 148 matrices at N = 1280) and ZLAQR0's NIBBLE */ int hess_streams = 1; int hess_graph = 1; /* replay the Hessenberg stage as one CUDA graph (0: individual launches) */ int evec_mode = 1; int lu_mode = 1; /* 1: blocked LU with DMMA updates, 0: v1 one-CTA kernel */ int hess_mode = 1; /* 0: v1 unblocked CTA kernel, 1: batched blocked + DMMA, 2: blocked, scalar GEMM */ } g_tune;
 
 int fail(const std::string& m) { g_err = m; return 1; }
 bool g_qrprof_on = false;
@@ -577,7 +577,7 @@ int run_eigen(stabgpu_plan* pl, int sort_mode, int scale_rows) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(pl->ev[ST_PREP + 1], s));
   {
-    HqrLaunch q; q.W = g_tune.W; q.ns_max = g_tune.ns; q.steps_max = g_tune.qr_steps; q.nw = g_tune.qr_nw; q.nibble = g_tune.qr_nibble;
+    HqrLaunch q; q.W = g_tune.W; q.ns_max = g_tune.ns; q.steps_max = g_tune.qr_steps; q.nw = g_tune.qr_nw >= 0 ? g_tune.qr_nw : (N > 640 ? 44 : 32); q.nibble = g_tune.qr_nibble;
     if (q.nw >= q.W || q.nw > 45 || (2 * q.nw + 1) * q.nw > q.W * (q.W + 1)) q.nw = 0;     // the window must fit the shared-memory tile
     if (q.W - 2 < 2 * q.ns_max - 1 || q.steps_max < 2 * q.ns_max - 1 || q.W - 2 * q.ns_max - 1 < 4)
       return fail("libstabgpu: invalid QR tuning (window too small for the shift count)");
