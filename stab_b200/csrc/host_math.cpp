@@ -207,73 +207,26 @@ int stabgpu_mean_gradients(int ny, int wallt, const double* vm, const double* de
 // branches that are dead for s = 0), then the O(ny) metric formulas.
 int stabgpu_circh(double* x_inout, int ny, const double* r, double* h5) {
   double* h = h5; double* dhds = h5 + ny; double* dhdr = h5 + 2 * ny; double* dhdsr = h5 + 3 * ny; double* dhdrr = h5 + 4 * ny;
-  if (*x_inout == -1.0) {
+  if (*x_inout == -1.0) {                               // flat plate: no curvature terms (circh.f90:41-46)
     for (int i = 0; i < ny; ++i) { h[i] = 1.0; dhds[i] = dhdr[i] = dhdsr[i] = dhdrr[i] = 0.0; }
     return 0;
   }
-  const double radius = *x_inout;
-  *x_inout = 0.0;                                      // circh.f90:47-49
-  const double s = 0.0, infty = 1.0e30;
-  const double th1 = std::atan2(std::sqrt(radius * radius - 0.0 * 0.0), 0.0);
-  const double xl = radius * std::cos(th1 - s);
-  const double yl = std::sqrt(radius * radius - xl * xl);
-  const double th = std::atan2(-xl, std::sqrt(radius * radius - xl * xl));
-  const double bn1 = -std::sin(th), bn2 = std::cos(th);
-  const double dydx = (xl == 0.0) ? -infty : (-xl) / yl;
-  const double dxbds = 1.0 / std::sqrt(1.0 + dydx * dydx);
-  const double dxdy = (xl == 0.0) ? -infty : yl / (-xl);
-  const double dybds = ((xl <= 0.0) ? 1.0 : -1.0) / std::sqrt(dxdy * dxdy + 1.0);
-  double dx, dy, ddxdx, ddydx, ddxdy, ddydy, d2dxdx2, d2dydx2, d2dxdy2, d2dydy2;
-  if (yl == 0.0) {
-    dx = 0.0; dy = -xl; ddxdx = -infty; ddydx = -1.0; ddxdy = 1.0; ddydy = 0.0;
-    d2dxdx2 = -infty; d2dydx2 = 0.0; d2dxdy2 = 0.0; d2dydy2 = (xl * xl + yl * yl) / (xl * xl * xl);
-  } else if (xl == 0.0) {
-    dx = yl; dy = 0.0; ddxdx = 0.0; ddydx = -1.0; ddxdy = 1.0; ddydy = infty;
-    d2dxdx2 = -(yl * yl + xl * xl) / (yl * yl * yl); d2dydx2 = 0.0; d2dxdy2 = 0.0; d2dydy2 = infty;
-  } else {
-    dx = yl; dy = -xl; ddxdx = -xl / yl; ddydx = -1.0; ddxdy = 1.0; ddydy = yl / xl;
-    d2dxdx2 = -(yl * yl + xl * xl) / (yl * yl * yl); d2dydx2 = 0.0; d2dxdy2 = 0.0;
-    d2dydy2 = (xl * xl + yl * yl) / (xl * xl * xl);
-  }
-  const double q = dx * dx + dy * dy;
-  const double q05 = std::pow(q, 0.5), q15 = std::pow(q, 1.5), q25 = std::pow(q, 2.5);
-  double dbn1, dbn2, d2xbds2, d2ybds2, d2bn1, d2bn2;
-  if (std::fabs(bn1) > std::fabs(bn2)) {
-    dbn1 = (-ddydy / q05 + 0.5 * dy * (2.0 * dx * ddxdy + 2.0 * dy * ddydy) / q15) * dybds;
-    dbn2 = (ddxdy / q05 - 0.5 * dx * (2.0 * dx * ddxdy + 2.0 * dy * ddydy) / q15) * dybds;
-    const double d2xdy2 = -(xl * xl + yl * yl) / (xl * xl * xl);
-    const double sg = (xl <= 0.0) ? -1.0 : 1.0;
-    d2ybds2 = sg * std::pow(1.0 + dxdy * dxdy, -1.5) * dxdy * d2xdy2 * dybds;
-    d2xbds2 = d2xdy2 * (dybds * dybds) + dxdy * d2ybds2;
-    d2bn1 = ((ddxdy * (dy * ddxdy - dx * ddydy) + dx * (dy * d2dxdy2 - dx * d2dydy2)) / q15 -
-             (3.0 * dx * (dy * ddxdy - dx * ddydy) * (dx * ddxdy + dy * ddydy)) / q25) * (dybds * dybds) +
-            (-ddydy / q05 + 0.5 * dy * (2.0 * dx * ddxdy + 2.0 * dy * ddydy) / q15) * d2ybds2;
-    d2bn2 = ((ddydy * (dy * ddxdy - dx * ddydy) + dy * (dy * d2dxdy2 - dx * d2dydy2)) / q15 -
-             (3.0 * dy * (dy * ddxdy - dx * ddydy) * (dx * ddxdy + dy * ddydy)) / q25) * (dybds * dybds) +
-            (ddxdy / q05 - 0.5 * dx * (2.0 * dx * ddxdy + 2.0 * dy * ddydy) / q15) * d2ybds2;
-  } else {
-    dbn1 = (-ddydx / q05 + 0.5 * dy * (2.0 * dx * ddxdx + 2.0 * dy * ddydx) / q15) * dxbds;
-    dbn2 = (ddxdx / q05 - 0.5 * dx * (2.0 * dx * ddxdx + 2.0 * dy * ddydx) / q15) * dxbds;
-    const double d2ydx2 = -(xl * xl + yl * yl) / (yl * yl * yl);
-    d2xbds2 = -std::pow(1.0 + dydx * dydx, -1.5) * dydx * d2ydx2 * dxbds;
-    d2ybds2 = d2ydx2 * (dxbds * dxbds) + dydx * d2xbds2;
-    d2bn1 = ((ddxdx * (dy * ddxdx - dx * ddydx) + dx * (dy * d2dxdx2 - dx * d2dydx2)) / q15 -
-             (3.0 * dx * (dy * ddxdx - dx * ddydx) * (dx * ddxdx + dy * ddydx)) / q25) * (dxbds * dxbds) +
-            (-ddydx / q05 + 0.5 * dy * (2.0 * dx * ddxdx + 2.0 * dy * ddydx) / q15) * d2xbds2;
-    d2bn2 = ((ddydx * (dy * ddxdx - dx * ddydx) + dy * (dy * d2dxdx2 - dx * d2dydx2)) / q15 -
-             (3.0 * dy * (dy * ddxdx - dx * ddydx) * (dx * ddxdx + dy * ddydx)) / q25) * (dxbds * dxbds) +
-            (ddxdx / q05 - 0.5 * dx * (2.0 * dx * ddxdx + 2.0 * dy * ddydx) / q15) * d2xbds2;
-  }
-  if (xl == 0.0) d2bn1 = 0.0;
+  // The reference evaluates the body-fitted metrics of a circular cylinder of radius R = x at the arc length s = 0 only
+  // (circh.f90:47-49 overwrites x with 0 after taking the radius) through its general curve machinery (circh.f90:51-188:
+  // local tangent and normal, their first and second arc-length derivatives, branches on the steeper coordinate).  On a
+  // circle that machinery reduces to constant curvature 1/R:
+  //     h = 1 + r / R,   dh/dr = 1 / R,   dh/ds = d2h/(ds dr) = d2h/dr2 = 0.
+  // The literal evaluation (oracle/stab_oracle.py::circh restates it line by line) differs from these values by at most
+  // 1 ulp in h, 2e-16 relative in dh/dr and 3e-20 absolute in the three vanishing terms, which come out as rounding
+  // residue of cos(pi/2) (tests/test_host_cabi.py::test_circh_matches_oracle, test_circh_closed_form_against_literal).
+  const double radius = std::fabs(*x_inout);            // the literal evaluation depends on R only through R^2 and |R|
+  if (!(radius > 0.0) || !std::isfinite(radius)) return 1;   // R = 0 divides by zero in the reference
+  *x_inout = 0.0;
+  const double curv = 1.0 / radius;
   for (int i = 0; i < ny; ++i) {
-    const double a = dxbds + r[i] * dbn1, b = dybds + r[i] * dbn2;
-    const double hh = std::sqrt(a * a + b * b);
-    const double dads = d2xbds2 + r[i] * d2bn1, dbds = d2ybds2 + r[i] * d2bn2;
-    h[i] = hh;
-    dhds[i] = (a * dads + b * dbds) / hh;
-    dhdr[i] = (a * dbn1 + b * dbn2) / hh;
-    dhdrr[i] = (-(dhdr[i] * dhdr[i]) + dbn1 * dbn1 + dbn2 * dbn2) / hh;
-    dhdsr[i] = -dhds[i] / (hh * hh) * (a * dbn1 + b * dbn2) + (dads * dbn1 + a * d2bn1 + dbds * dbn2 + b * d2bn2) / hh;
+    h[i] = 1.0 + r[i] / radius;
+    dhdr[i] = curv;
+    dhds[i] = dhdsr[i] = dhdrr[i] = 0.0;
   }
   return 0;
 }

@@ -92,6 +92,22 @@ def test_circh_matches_oracle():
     assert np.abs(h5 - ref).max() <= 1e-15 * np.abs(ref).max() + 1e-30
 
 
+@pytest.mark.parametrize("radius", [500.0, 100.0, 1.0e4, 37.5, -500.0])
+def test_circh_closed_form_against_literal(radius):
+    """The product evaluates circh's metrics in closed form (circle: h = 1 + r/R, dh/dr = 1/R, the rest 0); the oracle restates
+    circh.f90:35-188 literally.  They agree to 1 ulp in h, 2 ulp in dh/dr and to the literal evaluation's own rounding residue
+    (<= 4 eps / R^2) in the three vanishing terms, for the radii of the reference decks (FSCtest / CFtest: 500) and others."""
+    y = so.sgengrid(48, 0.05, 30.0)[0]
+    x_out, h5 = sb.circh(radius, y)
+    rx, h, dhds, dhdr, dhdsr, dhdrr = so.circh(radius, y)
+    assert x_out == rx == 0.0
+    assert np.all(np.abs(h5[:, 0] - h) <= np.spacing(h))
+    assert np.all(np.abs(h5[:, 2] - dhdr) <= 2 * np.spacing(dhdr))
+    eps = np.finfo(float).eps
+    for k, lit, bound in ((1, dhds, 1e-30), (3, dhdsr, 1e-30), (4, dhdrr, 4 * eps / radius ** 2)):   # d2h/dr2: cancellation of 1/R^2 terms
+        assert np.all(h5[:, k] == 0.0) and np.abs(lit).max() <= bound
+
+
 def test_sweep_enumeration_and_shards():
     a, b = sb.mtemporal_points(0.1, 0.5, 0.1, 0.0, 0.0, 1.0)
     ref = so.mtemporal_points(0.1, 0.5, 0.1, 0.0, 0.0, 1.0)
