@@ -736,7 +736,10 @@ int stabgpu_device_info(char* name, int name_len, int* sm_count, double* mem_gb)
 /* debug: cycle counters of the QR kernel for matrix 0 of the last run (not part of the public header) */
 int stabgpu_debug_qr_profile(int enable, long long* out16) {
   g_qrprof_on = enable != 0;
-  if (out16 && g_qrprof_dev) { cudaDeviceSynchronize(); cudaMemcpy(out16, g_qrprof_dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost); }
+  if (out16 && g_qrprof_dev) {
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out16, g_qrprof_dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 
@@ -1233,8 +1236,10 @@ int stabgpu_zgeev_batch(int n, int batch, const double* A, int want_vectors, dou
     rc = run_eigen(pl, 0, 0);
     if (!rc) rc = (cudaStreamSynchronize(pl->stream) != cudaSuccess);
     if (rc) { if (g_err.empty()) fail("libstabgpu: eigen pipeline failed"); break; }
-    cudaMemsetAsync(pl->info_lu.p, 0, sizeof(int) * m, pl->stream);
-    cudaStreamSynchronize(pl->stream);
+    if (cudaMemsetAsync(pl->info_lu.p, 0, sizeof(int) * m, pl->stream) != cudaSuccess || cudaStreamSynchronize(pl->stream) != cudaSuccess) {
+      rc = fail("libstabgpu: clearing the LU status failed");
+      break;
+    }
     rc = stabgpu_plan_download(pl, w + 2 * (size_t)p0 * n, want_vectors ? V + 2 * (size_t)p0 * st : nullptr, info ? info + p0 : nullptr);
   }
   {
