@@ -755,7 +755,10 @@ int stabgpu_set_tuning(int qr_window, int qr_shifts, int qr_threads, int hess_th
   if (qr_window > 0) g_tune.W = qr_window;
   if (qr_shifts > 0) g_tune.ns = qr_shifts;
   if (qr_threads > 0) g_tune.qr_threads = qr_threads;
-  if (hess_threads > 0) g_tune.hess_threads = hess_threads;
+  if (hess_threads > 0) {
+    if (hess_threads > 512 || hess_threads % 32) return fail("libstabgpu: hess_threads must be a multiple of 32 up to 512 (the panel-step kernel's launch bound)");
+    g_tune.hess_threads = hess_threads;
+  }
   return 0;
 }
 
