@@ -179,18 +179,31 @@ def config_dict(args, npts):
 # ---- clocks sampler -------------------------------------------------------------------------------
 class Clocks:
     def __init__(self, dev):
-        self.dev, self.rows, self.stop = dev, [], False
+        self.dev, self.rows, self.stop, self.proc = dev, [], False, None
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+        base = ["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"]
+        # one streaming nvidia-smi (a sample every 100 ms) instead of one process per sample: a 3-step timed region of
+        # ~0.9 s then holds ~8 samples rather than 1-2
+        try:
+            self.proc = subprocess.Popen(base + ["-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+                if self.stop:
+                    break
+            return
+        except Exception:
+            self.proc = None
         while not self.stop:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                o = subprocess.run(base, capture_output=True, text=True, timeout=5).stdout.strip()
                 if o:
-                    self.rows.append([s.strip() for s in o.split(",")])
+                    self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
             time.sleep(0.2)
@@ -201,6 +214,15 @@ class Clocks:
 
     def __exit__(self, *a):
         self.stop = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                self.proc.wait(timeout=3)
+            except Exception:
+                try:
+                    self.proc.kill()
+                except Exception:
+                    pass
         self.t.join(timeout=6)
 
     def summary(self):
